@@ -1,0 +1,106 @@
+"""ctypes binding of libdgr_b200.so (the C ABI declared in include/dgr_b200.h).
+
+There is NO fallback: if the shared library is missing or does not load, importing the compute entry points raises.
+The library is built in-tree by ``dreamgaussian_b200.build`` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+c_f32p = ctypes.c_void_p  # device pointers travel as integers
+
+
+class DgrSettings(ctypes.Structure):
+    _fields_ = [
+        ("image_height", ctypes.c_int32), ("image_width", ctypes.c_int32),
+        ("tanfovx", ctypes.c_float), ("tanfovy", ctypes.c_float), ("scale_modifier", ctypes.c_float),
+        ("sh_degree", ctypes.c_int32), ("prefiltered", ctypes.c_int32), ("debug", ctypes.c_int32),
+        ("bg", c_f32p), ("viewmatrix", c_f32p), ("projmatrix", c_f32p), ("campos", c_f32p),
+    ]
+
+
+class DgrGaussians(ctypes.Structure):
+    _fields_ = [
+        ("P", ctypes.c_int32), ("M", ctypes.c_int32),
+        ("means3D", c_f32p), ("shs", c_f32p), ("colors_precomp", c_f32p), ("opacities", c_f32p),
+        ("scales", c_f32p), ("rotations", c_f32p), ("cov3D_precomp", c_f32p),
+    ]
+
+
+class DgrImages(ctypes.Structure):
+    _fields_ = [("color", c_f32p), ("depth", c_f32p), ("alpha", c_f32p), ("radii", ctypes.c_void_p)]
+
+
+class DgrImageGrads(ctypes.Structure):
+    _fields_ = [("dL_dcolor", c_f32p), ("dL_ddepth", c_f32p), ("dL_dalpha", c_f32p)]
+
+
+class DgrGaussianGrads(ctypes.Structure):
+    _fields_ = [
+        ("dL_dmeans3D", c_f32p), ("dL_dmeans2D", c_f32p), ("dL_dshs", c_f32p), ("dL_dcolors_precomp", c_f32p),
+        ("dL_dopacities", c_f32p), ("dL_dscales", c_f32p), ("dL_drotations", c_f32p), ("dL_dcov3D_precomp", c_f32p),
+        ("accumulate", ctypes.c_int32),
+    ]
+
+
+EXPORTS = (
+    "dgr_abi_version", "dgr_last_error", "dgr_launch_count", "dgr_reset_launch_count",
+    "dgr_geom_bytes", "dgr_image_bytes", "dgr_binning_bytes",
+    "dgr_forward_preprocess", "dgr_forward_render", "dgr_backward", "dgr_mark_visible", "dgr_debug_geom",
+)
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load libdgr_b200.so (building it first if nvcc is available and the sources are newer). Raises on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if _build.is_stale():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this machine and no prebuilt library: nothing to fall back to
+            if not os.path.exists(path):
+                raise RuntimeError(
+                    "libdgr_b200.so is not built and could not be compiled here (%s). "
+                    "Run `python -m dreamgaussian_b200.build` on a machine with nvcc." % e)
+    lib = ctypes.CDLL(path)
+    vp, u64, i32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int32
+    lib.dgr_abi_version.restype = ctypes.c_int
+    lib.dgr_last_error.restype = ctypes.c_char_p
+    lib.dgr_launch_count.restype = u64
+    lib.dgr_reset_launch_count.restype = None
+    lib.dgr_geom_bytes.restype = ctypes.c_size_t
+    lib.dgr_geom_bytes.argtypes = [i32]
+    lib.dgr_image_bytes.restype = ctypes.c_size_t
+    lib.dgr_image_bytes.argtypes = [i32, i32]
+    lib.dgr_binning_bytes.restype = ctypes.c_size_t
+    lib.dgr_binning_bytes.argtypes = [u64, i32, i32]
+    lib.dgr_forward_preprocess.restype = ctypes.c_int
+    lib.dgr_forward_preprocess.argtypes = [ctypes.POINTER(DgrSettings), ctypes.POINTER(DgrGaussians), vp, vp, vp, vp]
+    lib.dgr_forward_render.restype = ctypes.c_int
+    lib.dgr_forward_render.argtypes = [ctypes.POINTER(DgrSettings), ctypes.POINTER(DgrGaussians), vp, vp, u64, vp,
+                                       ctypes.POINTER(DgrImages), vp]
+    lib.dgr_backward.restype = ctypes.c_int
+    lib.dgr_backward.argtypes = [ctypes.POINTER(DgrSettings), ctypes.POINTER(DgrGaussians), vp, vp, u64, vp, vp, vp,
+                                 ctypes.POINTER(DgrImageGrads), ctypes.POINTER(DgrGaussianGrads), vp]
+    lib.dgr_mark_visible.restype = ctypes.c_int
+    lib.dgr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
+    lib.dgr_debug_geom.restype = ctypes.c_int
+    lib.dgr_debug_geom.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    if lib.dgr_abi_version() != 1:
+        raise RuntimeError("libdgr_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        raise RuntimeError("libdgr_b200: %s (code %d)" % (load().dgr_last_error().decode(), code))

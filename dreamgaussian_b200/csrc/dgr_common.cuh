@@ -1,0 +1,116 @@
+// dgr_common.cuh — shared definitions of the sm_100a rasterizer kernels: scratch layouts, PTX wrappers
+// (mbarrier + 1-D bulk TMA), small math helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/dgr_constants.h"
+
+namespace dgr {
+
+constexpr int kTile = DGR_TILE;            // 16 x 16 pixel tiles
+constexpr int kTileThreads = 256;          // one thread per pixel
+constexpr int kPreThreads = 256;           // per-Gaussian kernels
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-Gaussian record produced by the forward preprocess and consumed (through the depth-sorted, per-tile
+// contiguous copy) by both render kernels.  48 bytes = 3 x float4 so a tile's instance range is one contiguous,
+// 16-byte aligned block that a single cp.async.bulk (TMA) moves into shared memory.
+//   q0 = { mean_px.x, mean_px.y, -0.5 conicA log2e, -conicB log2e }
+//   q1 = { -0.5 conicC log2e, opacity, depth (view z), aabb_x = x0 | x1 << 16 }
+//   q2 = { r, g, b, aabb_y = y0 | y1 << 16 }
+// The conic is stored as the coefficients of power*log2(e), so power2 = dx (q0.z dx + q0.w dy) + q1.x dy^2 is
+// 5 instructions and alpha = o * ex2(power2) needs no extra multiply.  aabb = inclusive pixel
+// bounds of { pixels whose 16x16 tile is in the 3-sigma tile rect } ∩ { bounding box of alpha >= 1/255 },
+// i.e. a conservative superset of the pixels this Gaussian can contribute to under the reference's rules.
+// ---------------------------------------------------------------------------------------------------------
+struct __align__(16) Rec { float4 q0, q1, q2; };
+static_assert(sizeof(Rec) == 48, "Rec must be 48 bytes");
+
+// Per-Gaussian reduction target of the backward render: 12 floats (3 x float4)
+//   0 m0 = sum u            1 m1 = sum u dx        2 m2 = sum u dy
+//   3 m3 = sum u dx^2       4 m4 = sum u dx dy     5 m5 = sum u dy^2
+//   6..8 sum w * dL/dC[rgb] 9 sum w * dL/dD        10, 11 unused
+// with u = o * G * dL/dalpha, w = alpha * T, d = mean_px - pixel.
+constexpr int kGradRecFloats = 12;
+
+struct GeomHeader {
+    unsigned long long n_inst;     // total tile instances of this frame
+    unsigned int ticket;           // dynamic block id counter of the preprocess kernel
+    unsigned int pad[13];
+};
+static_assert(sizeof(GeomHeader) == 64, "GeomHeader");
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// geom scratch: [header 256][status u64 x nblocks][rec 48 x P][offsets u32 x P][touched u32 x P]
+struct GeomLayout {
+    size_t off_status, off_rec, off_offsets, off_touched, total;
+    int nblocks;
+    __host__ __device__ explicit GeomLayout(int P) {
+        nblocks = (P + kPreThreads - 1) / kPreThreads;
+        if (nblocks < 1) nblocks = 1;
+        size_t Pn = P > 0 ? (size_t)P : 1;
+        size_t o = 256;
+        off_status = o;  o = align_up(o + (size_t)nblocks * 8, 256);
+        off_rec = o;     o = align_up(o + Pn * sizeof(Rec), 256);
+        off_offsets = o; o = align_up(o + Pn * 4, 256);
+        off_touched = o; o = align_up(o + Pn * 4, 256);
+        total = o;
+    }
+};
+
+// image scratch: [ranges uint2 x tiles][n_contrib u32 x H*W]
+struct ImageLayout {
+    size_t off_ranges, off_ncontrib, total;
+    int gx, gy;
+    __host__ __device__ ImageLayout(int H, int W) {
+        gx = (W + kTile - 1) / kTile; gy = (H + kTile - 1) / kTile;
+        size_t tiles = (size_t)gx * gy; if (tiles < 1) tiles = 1;
+        size_t hw = (size_t)H * W; if (hw < 1) hw = 1;
+        size_t o = 0;
+        off_ranges = o;   o = align_up(o + tiles * 8, 256);
+        off_ncontrib = o; o = align_up(o + hw * 4, 256);
+        total = o;
+    }
+};
+
+// ------------------------------------------------ PTX wrappers ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// 1-D bulk TMA: global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ void red_add_f32(float *addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 ldg_f4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// status word of the decoupled look-back scan: [63:62] flag, [61:0] value
+enum : unsigned long long { kFlagAggregate = 1ull << 62, kFlagPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1 };
+
+}  // namespace dgr

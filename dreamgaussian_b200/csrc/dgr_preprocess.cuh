@@ -1,0 +1,299 @@
+// dgr_preprocess.cuh — per-Gaussian forward kernel (A2 of SURVEY.md §8a): frustum cull, cov3D, EWA cov2D, conic,
+// radius, pixel mean, SH -> RGB, opacity-aware pixel AABB, and — fused — the exclusive prefix sum of the per-Gaussian
+// tile counts (single-pass decoupled look-back), so the op needs no separate scan kernel and no CUB.
+// Streaming, HBM-bound: reads 44 + 12 M bytes, writes 60 bytes per Gaussian.
+//
+// Reference behaviour restated (not copied): the `preprocessCUDA` step of the op called at
+// /root/reference/gs_renderer.py:800-809; maths anchors: gs_renderer.py:85-132 (R, cov3D), sh_utils.py:57-100 (SH).
+#pragma once
+#include "dgr_common.cuh"
+
+namespace dgr {
+
+struct FrameConsts {            // staged in shared memory once per block
+    float V[16], PM[16], cam[3], pad;
+};
+
+__device__ __forceinline__ void load_frame(FrameConsts &fc, const float *V, const float *PM, const float *cam) {
+    int t = threadIdx.x;
+    if (t < 16) fc.V[t] = __ldg(V + t);
+    else if (t < 32) fc.PM[t - 16] = __ldg(PM + t - 16);
+    else if (t < 35 && cam) fc.cam[t - 32] = __ldg(cam + t - 32);
+}
+
+__device__ __forceinline__ void quat_to_R(const float4 q, float (&R)[9]) {
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - r * z); R[2] = 2.f * (x * z + r * y);
+    R[3] = 2.f * (x * y + r * z); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - r * x);
+    R[6] = 2.f * (x * z - r * y); R[7] = 2.f * (y * z + r * x); R[8] = 1.f - 2.f * (x * x + y * y);
+}
+
+// Sigma = (R S)(R S)^T packed xx,xy,xz,yy,yz,zz
+__device__ __forceinline__ void cov3d_from_scale_rot(const float3 s, const float (&R)[9], float (&S6)[6]) {
+    float M[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { M[3 * i] = R[3 * i] * s.x; M[3 * i + 1] = R[3 * i + 1] * s.y; M[3 * i + 2] = R[3 * i + 2] * s.z; }
+    S6[0] = M[0] * M[0] + M[1] * M[1] + M[2] * M[2];
+    S6[1] = M[0] * M[3] + M[1] * M[4] + M[2] * M[5];
+    S6[2] = M[0] * M[6] + M[1] * M[7] + M[2] * M[8];
+    S6[3] = M[3] * M[3] + M[4] * M[4] + M[5] * M[5];
+    S6[4] = M[3] * M[6] + M[4] * M[7] + M[5] * M[8];
+    S6[5] = M[6] * M[6] + M[7] * M[7] + M[8] * M[8];
+}
+
+// SH basis values for a unit direction (sh_utils.py:74-100), b[0..(DEG+1)^2)
+template <int DEG>
+__device__ __forceinline__ void sh_basis(float x, float y, float z, float (&b)[16]) {
+    b[0] = DGR_SH_C0;
+    if (DEG > 0) {
+        b[1] = -DGR_SH_C1 * y; b[2] = DGR_SH_C1 * z; b[3] = -DGR_SH_C1 * x;
+        if (DEG > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            b[4] = DGR_SH_C2_0 * xy; b[5] = DGR_SH_C2_1 * yz; b[6] = DGR_SH_C2_2 * (2.f * zz - xx - yy);
+            b[7] = DGR_SH_C2_3 * xz; b[8] = DGR_SH_C2_4 * (xx - yy);
+            if (DEG > 2) {
+                b[9] = DGR_SH_C3_0 * y * (3.f * xx - yy);
+                b[10] = DGR_SH_C3_1 * xy * z;
+                b[11] = DGR_SH_C3_2 * y * (4.f * zz - xx - yy);
+                b[12] = DGR_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                b[13] = DGR_SH_C3_4 * x * (4.f * zz - xx - yy);
+                b[14] = DGR_SH_C3_5 * z * (xx - yy);
+                b[15] = DGR_SH_C3_6 * x * (xx - 3.f * yy);
+            }
+        }
+    }
+}
+
+// Load the first 3*(DEG+1)^2 floats of one Gaussian's SH row ([M][3] layout) with 128-bit loads when the row is
+// 16-byte aligned (M % 4 == 0: the deg-1 and deg-3 tensors), scalar otherwise.
+template <int DEG>
+__device__ __forceinline__ void load_sh_row(const float *row, bool vec, float (&c)[48]) {
+    constexpr int NF = 3 * (DEG + 1) * (DEG + 1);
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < (NF + 3) / 4; i++) {
+            if (4 * i + 3 < NF) {
+                const float4 v = ldg_f4(row + 4 * i);
+                c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (4 * i + j < NF) c[4 * i + j] = __ldg(row + 4 * i + j);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NF; i++) c[i] = __ldg(row + i);
+    }
+}
+
+// Geometry shared by forward and backward: everything up to cov2D for one Gaussian.
+struct Geo {
+    float t[3];          // view-space position
+    float tx, ty;        // clamped*tz (used in J only)
+    bool clx, cly;       // tx/tz, ty/tz were clamped
+    float T0[3], T1[3];  // rows of T = J * Rwv
+    float cxx, cxy, cyy; // cov2D incl. low-pass
+    float ndcx, ndcy, pw;
+};
+
+__device__ __forceinline__ void project_geo(const FrameConsts &fc, const float3 p, const float (&S6)[6],
+                                            float fx, float fy, float limx, float limy, Geo &g) {
+    const float *V = fc.V, *PM = fc.PM;
+#pragma unroll
+    for (int i = 0; i < 3; i++) g.t[i] = p.x * V[i] + p.y * V[4 + i] + p.z * V[8 + i] + V[12 + i];
+    float ph[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) ph[i] = p.x * PM[i] + p.y * PM[4 + i] + p.z * PM[8 + i] + PM[12 + i];
+    g.pw = 1.f / (ph[3] + DGR_W_EPS);
+    g.ndcx = ph[0] * g.pw; g.ndcy = ph[1] * g.pw;
+    const float tz = g.t[2];
+    const float txtz = g.t[0] / tz, tytz = g.t[1] / tz;
+    g.clx = (txtz < -limx) || (txtz > limx);
+    g.cly = (tytz < -limy) || (tytz > limy);
+    g.tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+    g.ty = fminf(limy, fmaxf(-limy, tytz)) * tz;
+    const float J00 = fx / tz, J02 = -(fx * g.tx) / (tz * tz), J11 = fy / tz, J12 = -(fy * g.ty) / (tz * tz);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        g.T0[k] = J00 * V[4 * k] + J02 * V[4 * k + 2];
+        g.T1[k] = J11 * V[4 * k + 1] + J12 * V[4 * k + 2];
+    }
+    const float Sg[9] = { S6[0], S6[1], S6[2], S6[1], S6[3], S6[4], S6[2], S6[4], S6[5] };
+    float ST0[3], ST1[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        ST0[k] = Sg[3 * k] * g.T0[0] + Sg[3 * k + 1] * g.T0[1] + Sg[3 * k + 2] * g.T0[2];
+        ST1[k] = Sg[3 * k] * g.T1[0] + Sg[3 * k + 1] * g.T1[1] + Sg[3 * k + 2] * g.T1[2];
+    }
+    g.cxx = g.T0[0] * ST0[0] + g.T0[1] * ST0[1] + g.T0[2] * ST0[2] + DGR_COV2D_LOWPASS;
+    g.cxy = g.T0[0] * ST1[0] + g.T0[1] * ST1[1] + g.T0[2] * ST1[2];
+    g.cyy = g.T1[0] * ST1[0] + g.T1[1] * ST1[1] + g.T1[2] * ST1[2] + DGR_COV2D_LOWPASS;
+}
+
+// Block-wide exclusive scan of one unsigned per thread + decoupled look-back across blocks (ticket order).
+// Returns this thread's global exclusive prefix; the last block also publishes the grand total.
+__device__ __forceinline__ unsigned long long scan_lookback(unsigned val, unsigned ticket, int nblocks,
+                                                           unsigned long long *status, unsigned long long *total_out) {
+    __shared__ unsigned s_warp[kPreThreads / 32];
+    __shared__ unsigned long long s_block_prefix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned inc = val;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned warp_off = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < kPreThreads / 32; w++) { unsigned v = s_warp[w]; if (w < warp) warp_off += v; block_total += v; }
+    if (warp == 0) {
+        volatile unsigned long long *st = status;
+        const unsigned long long agg = block_total;
+        unsigned long long excl = 0;
+        if (ticket == 0) {
+            if (lane == 0) { st[0] = kFlagPrefix | agg; }
+        } else {
+            if (lane == 0) { st[ticket] = kFlagAggregate | agg; }
+            int base = (int)ticket - 1;
+            while (true) {
+                const int idx = base - lane;
+                const unsigned long long s = (idx >= 0) ? st[idx] : kFlagPrefix;
+                const unsigned flag = (unsigned)(s >> 62);
+                const unsigned m_inv = __ballot_sync(0xffffffffu, flag == 0);
+                const unsigned m_pre = __ballot_sync(0xffffffffu, flag == 2);
+                const int fp = m_pre ? (__ffs(m_pre) - 1) : 32;
+                const unsigned upto = (fp >= 31) ? 0xffffffffu : ((2u << fp) - 1u);
+                if (m_inv & upto) continue;                       // a needed predecessor has not published yet
+                unsigned long long v = (lane <= fp) ? (s & kValueMask) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                excl += v;
+                if (fp < 32) break;
+                base -= 32;
+            }
+            if (lane == 0) { __threadfence(); st[ticket] = kFlagPrefix | (excl + agg); }
+        }
+        if (lane == 0) {
+            s_block_prefix = excl;
+            if ((int)ticket == nblocks - 1) *total_out = excl + agg;
+        }
+    }
+    __syncthreads();
+    return s_block_prefix + warp_off + (inc - val);
+}
+
+template <int DEG, bool HAS_SH, bool HAS_COV>
+__global__ void __launch_bounds__(kPreThreads)
+preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, float scale_modifier,
+                      const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
+                      const float *__restrict__ campos,
+                      const float *__restrict__ means3D, const float *__restrict__ shs,
+                      const float *__restrict__ colors_precomp, const float *__restrict__ opacities,
+                      const float *__restrict__ scales, const float *__restrict__ rotations,
+                      const float *__restrict__ cov3D_precomp,
+                      int *__restrict__ radii, GeomHeader *__restrict__ hdr, unsigned long long *__restrict__ status,
+                      Rec *__restrict__ rec, unsigned *__restrict__ offsets, unsigned *__restrict__ touched_out,
+                      int nblocks) {
+    __shared__ FrameConsts fc;
+    __shared__ unsigned s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&hdr->ticket, 1u);
+    load_frame(fc, viewmatrix, projmatrix, HAS_SH ? campos : nullptr);
+    __syncthreads();
+    const unsigned ticket = s_ticket;
+    const int g = (int)(ticket * kPreThreads + threadIdx.x);
+    unsigned touched = 0;
+    if (g < P) {
+        int radius_out = 0;
+        Rec r;
+        r.q0 = make_float4(0.f, 0.f, 0.f, 0.f); r.q1 = r.q0; r.q2 = r.q0;
+        const float3 p = make_float3(__ldg(means3D + 3 * (size_t)g), __ldg(means3D + 3 * (size_t)g + 1), __ldg(means3D + 3 * (size_t)g + 2));
+        const float tzc = p.x * fc.V[2] + p.y * fc.V[6] + p.z * fc.V[10] + fc.V[14];
+        if (tzc > DGR_NEAR_CULL_Z) {
+            float S6[6];
+            if (HAS_COV) {
+#pragma unroll
+                for (int i = 0; i < 6; i++) S6[i] = __ldg(cov3D_precomp + 6 * (size_t)g + i);
+            } else {
+                const float3 s = make_float3(scale_modifier * __ldg(scales + 3 * (size_t)g), scale_modifier * __ldg(scales + 3 * (size_t)g + 1),
+                                             scale_modifier * __ldg(scales + 3 * (size_t)g + 2));
+                float R[9]; quat_to_R(ldg_f4(rotations + 4 * (size_t)g), R);
+                cov3d_from_scale_rot(s, R, S6);
+            }
+            const float fx = (float)W / (2.f * tanfovx), fy = (float)H / (2.f * tanfovy);
+            Geo geo;
+            project_geo(fc, p, S6, fx, fy, DGR_FOV_CLAMP * tanfovx, DGR_FOV_CLAMP * tanfovy, geo);
+            const float det = geo.cxx * geo.cyy - geo.cxy * geo.cxy;
+            const float mid = 0.5f * (geo.cxx + geo.cyy);
+            const float lam = mid + sqrtf(fmaxf(DGR_EIG_FLOOR, mid * mid - det));
+            const float rad_f = ceilf(DGR_RADIUS_SIGMAS * sqrtf(lam));
+            const float mx = ((geo.ndcx + 1.f) * (float)W - 1.f) * 0.5f;
+            const float my = ((geo.ndcy + 1.f) * (float)H - 1.f) * 0.5f;
+            // det == 0 is the reference's cull; NaN / non-finite states (undefined upstream) are culled too.
+            const bool finite_ok = (det > 0.f) && (fabsf(mx) < 1e9f) && (fabsf(my) < 1e9f) && (rad_f < 1e9f);
+            if (finite_ok) {
+                const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
+                // 3-sigma tile rect, truncation toward zero then clamp (reference rule)
+                const int rminx = min(gx, max(0, (int)((mx - rad_f) / kTile)));
+                const int rminy = min(gy, max(0, (int)((my - rad_f) / kTile)));
+                const int rmaxx = min(gx, max(0, (int)((mx + rad_f + (kTile - 1)) / kTile)));
+                const int rmaxy = min(gy, max(0, (int)((my + rad_f + (kTile - 1)) / kTile)));
+                if (rmaxx > rminx && rmaxy > rminy) {
+                    radius_out = (int)rad_f;
+                    const float o = __ldg(opacities + g);
+                    // colour
+                    float cr, cg, cb;
+                    if (HAS_SH) {
+                        float dx = p.x - fc.cam[0], dy = p.y - fc.cam[1], dz = p.z - fc.cam[2];
+                        const float il = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
+                        dx *= il; dy *= il; dz *= il;
+                        float b[16]; sh_basis<DEG>(dx, dy, dz, b);
+                        float c[48];
+                        load_sh_row<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, c);
+                        cr = 0.f; cg = 0.f; cb = 0.f;
+#pragma unroll
+                        for (int k = 0; k < (DEG + 1) * (DEG + 1); k++) { cr += b[k] * c[3 * k]; cg += b[k] * c[3 * k + 1]; cb += b[k] * c[3 * k + 2]; }
+                        cr = fmaxf(cr + DGR_SH_OFFSET, 0.f); cg = fmaxf(cg + DGR_SH_OFFSET, 0.f); cb = fmaxf(cb + DGR_SH_OFFSET, 0.f);
+                    } else {
+                        cr = __ldg(colors_precomp + 3 * (size_t)g); cg = __ldg(colors_precomp + 3 * (size_t)g + 1); cb = __ldg(colors_precomp + 3 * (size_t)g + 2);
+                    }
+                    const float di = 1.f / det;
+                    const float cA = geo.cyy * di, cB = -geo.cxy * di, cC = geo.cxx * di;
+                    // opacity-aware pixel AABB: alpha >= 1/255  <=>  d^T conic d <= 2 ln(255 o)
+                    int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;
+                    const float o255 = o * 255.f;
+                    if (o255 > 1.f) {
+                        const float tau = 2.f * logf(o255);
+                        const float ex = sqrtf(tau * geo.cxx) * 1.0005f + 0.02f;
+                        const float ey = sqrtf(tau * geo.cyy) * 1.0005f + 0.02f;
+                        const float lim = 1e9f;
+                        bx0 = max(rminx * kTile, (int)ceilf(fmaxf(mx - ex, -lim)));
+                        by0 = max(rminy * kTile, (int)ceilf(fmaxf(my - ey, -lim)));
+                        bx1 = min(min(rmaxx * kTile, W) - 1, (int)floorf(fminf(mx + ex, lim)));
+                        by1 = min(min(rmaxy * kTile, H) - 1, (int)floorf(fminf(my + ey, lim)));
+                    }
+                    if (bx0 <= bx1 && by0 <= by1) {
+                        touched = (unsigned)(((bx1 >> 4) - (bx0 >> 4) + 1) * ((by1 >> 4) - (by0 >> 4) + 1));
+                    } else { bx0 = 1; bx1 = 0; by0 = 1; by1 = 0; }
+                    // conic stored as the coefficients of power*log2(e): -0.5 A log2e, -B log2e, -0.5 C log2e
+                    r.q0 = make_float4(mx, my, cA * (-0.5f * kLog2e), cB * (-kLog2e));
+                    r.q1 = make_float4(cC * (-0.5f * kLog2e), o, geo.t[2], __uint_as_float((unsigned)bx0 | ((unsigned)bx1 << 16)));
+                    r.q2 = make_float4(cr, cg, cb, __uint_as_float((unsigned)by0 | ((unsigned)by1 << 16)));
+                }
+            }
+        }
+        radii[g] = radius_out;
+        rec[g] = r;
+        touched_out[g] = touched;
+    }
+    const unsigned long long excl = scan_lookback(touched, ticket, nblocks, status, &hdr->n_inst);
+    if (g < P) offsets[g] = (unsigned)excl;
+}
+
+__global__ void mark_visible_kernel(int P, const float *__restrict__ means3D, const float *__restrict__ V, unsigned char *present) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P) return;
+    const float tz = __ldg(means3D + 3 * (size_t)g) * __ldg(V + 2) + __ldg(means3D + 3 * (size_t)g + 1) * __ldg(V + 6) +
+                     __ldg(means3D + 3 * (size_t)g + 2) * __ldg(V + 10) + __ldg(V + 14);
+    present[g] = tz > DGR_NEAR_CULL_Z ? 1 : 0;
+}
+
+}  // namespace dgr

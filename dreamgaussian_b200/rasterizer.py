@@ -1,0 +1,205 @@
+"""Host-side mirror of the reference's rasterizer operator: ``GaussianRasterizationSettings`` / ``GaussianRasterizer``.
+
+Drop-in for the import at /root/reference/gs_renderer.py:10-13 and the call at gs_renderer.py:745-809:
+
+    rasterizer = GaussianRasterizer(raster_settings=GaussianRasterizationSettings(...12 fields...))
+    color, radii, depth, alpha = rasterizer(means3D=, means2D=, shs=, colors_precomp=, opacities=,
+                                            scales=, rotations=, cov3D_precomp=)
+
+Same names, argument meaning, return shapes/dtypes (color [3,H,W], radii int32 [P], depth [1,H,W], alpha [1,H,W]) and
+error behaviour (the two "Please provide ..." exceptions) as the un-vendored package the reference imports [EXT].
+All arithmetic runs in libdgr_b200.so (hand-written sm_100a CUDA) through the C ABI of include/dgr_b200.h; torch is
+used for device memory, the current stream and autograd plumbing only.  There is no CPU path: non-CUDA tensors raise.
+"""
+import ctypes
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError(
+            "%s is on %s: this rasterizer has no CPU path (it runs as sm_100a CUDA kernels in libdgr_b200.so)" % (name, t.device))
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _opt(t, name):
+    if t is None or (isinstance(t, torch.Tensor) and t.numel() == 0 and t.dim() <= 1):
+        return None
+    return _dev_f32(t, name)
+
+
+class _Frame:
+    """ctypes views of one forward call's settings + inputs (keeps the tensors alive)."""
+
+    def __init__(self, rs: GaussianRasterizationSettings, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D):
+        self.keep = []
+        k = self.keep.append
+        self.bg = _dev_f32(rs.bg, "bg"); k(self.bg)
+        self.view = _dev_f32(rs.viewmatrix, "viewmatrix"); k(self.view)
+        self.proj = _dev_f32(rs.projmatrix, "projmatrix"); k(self.proj)
+        self.campos = _dev_f32(rs.campos, "campos"); k(self.campos)
+        if self.bg.numel() != 3 or self.view.numel() != 16 or self.proj.numel() != 16 or self.campos.numel() != 3:
+            raise ValueError("bg/campos must have 3 elements, viewmatrix/projmatrix 16")
+        self.settings = _lib.DgrSettings(
+            int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier),
+            int(rs.sh_degree), int(bool(rs.prefiltered)), int(bool(rs.debug)),
+            _ptr(self.bg), _ptr(self.view), _ptr(self.proj), _ptr(self.campos))
+        if means3D.dim() != 2 or means3D.shape[1] != 3:
+            raise ValueError("means3D must have dimensions (num_points, 3)")
+        P = means3D.shape[0]
+        M = 0
+        if sh is not None:
+            if sh.dim() != 3 or sh.shape[0] != P or sh.shape[2] != 3:
+                raise ValueError("shs must have dimensions (num_points, num_coeffs, 3)")
+            M = sh.shape[1]
+        for t, n, w in ((colors_precomp, "colors_precomp", 3), (scales, "scales", 3), (rotations, "rotations", 4), (cov3D, "cov3D_precomp", 6)):
+            if t is not None and (t.numel() != P * w):
+                raise ValueError("%s must have dimensions (num_points, %d)" % (n, w))
+        if opacities.numel() != P:
+            raise ValueError("opacities must have dimensions (num_points, 1)")
+        self.P, self.M = P, M
+        self.gaussians = _lib.DgrGaussians(P, M, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
+                                           _ptr(scales), _ptr(rotations), _ptr(cov3D))
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+        lib = _lib.load()
+        rs = raster_settings
+        means3D = _dev_f32(means3D, "means3D")
+        opacities = _dev_f32(opacities, "opacities")
+        sh, colors_precomp = _opt(sh, "shs"), _opt(colors_precomp, "colors_precomp")
+        scales, rotations, cov3D = _opt(scales, "scales"), _opt(rotations, "rotations"), _opt(cov3Ds_precomp, "cov3D_precomp")
+        dev = means3D.device
+        with torch.cuda.device(dev):
+            fr = _Frame(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D)
+            H, W, P = int(rs.image_height), int(rs.image_width), fr.P
+            u8 = dict(dtype=torch.uint8, device=dev)
+            color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+            depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+            alpha = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+            radii = torch.empty((P,), dtype=torch.int32, device=dev)
+            geom = torch.empty((lib.dgr_geom_bytes(P),), **u8)
+            image = torch.empty((lib.dgr_image_bytes(H, W),), **u8)
+            n_host = torch.zeros((1,), dtype=torch.int64).pin_memory()
+            st = _stream_ptr(dev)
+            _lib.check(lib.dgr_forward_preprocess(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(radii),
+                                                  ctypes.c_void_p(n_host.data_ptr()), st))
+            torch.cuda.current_stream(dev).synchronize()
+            n_inst = int(n_host.item())
+            binning = torch.empty((lib.dgr_binning_bytes(n_inst, H, W),), **u8) if n_inst > 0 else None
+            out = _lib.DgrImages(_ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii))
+            _lib.check(lib.dgr_forward_render(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(binning),
+                                              ctypes.c_uint64(n_inst), _ptr(image), ctypes.byref(out), st))
+        ctx.raster_settings = rs
+        ctx.num_rendered = n_inst
+        ctx.has = (sh is not None, colors_precomp is not None, scales is not None, cov3D is not None)
+        ctx.scratch = (geom, binning, image)
+        none = means3D.new_empty(0)
+        ctx.save_for_backward(means3D, sh if sh is not None else none, colors_precomp if colors_precomp is not None else none,
+                              opacities, scales if scales is not None else none, rotations if rotations is not None else none,
+                              cov3D if cov3D is not None else none, radii, alpha)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, depth, alpha
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
+        lib = _lib.load()
+        rs = ctx.raster_settings
+        means3D, sh, colors_precomp, opacities, scales, rotations, cov3D, radii, alpha = ctx.saved_tensors
+        has_sh, has_col, has_scale, has_cov = ctx.has
+        sh = sh if has_sh else None
+        colors_precomp = colors_precomp if has_col else None
+        scales = scales if has_scale else None
+        rotations = rotations if has_scale else None
+        cov3D = cov3D if has_cov else None
+        geom, binning, image = ctx.scratch
+        dev = means3D.device
+        with torch.cuda.device(dev):
+            fr = _Frame(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D)
+            P, M = fr.P, fr.M
+            f32 = dict(dtype=torch.float32, device=dev)
+            gC = _dev_f32(grad_color, "grad_color") if grad_color is not None else None
+            gD = _dev_f32(grad_depth, "grad_depth") if grad_depth is not None else None
+            gA = _dev_f32(grad_alpha, "grad_alpha") if grad_alpha is not None else None
+            d_means3D = torch.empty((P, 3), **f32)
+            d_means2D = torch.empty((P, 3), **f32)
+            d_opac = torch.empty((P, 1), **f32)
+            d_sh = torch.empty((P, M, 3), **f32) if has_sh else None
+            d_col = torch.empty((P, 3), **f32) if has_col else None
+            d_scales = torch.empty((P, 3), **f32) if has_scale else None
+            d_rot = torch.empty((P, 4), **f32) if has_scale else None
+            d_cov = torch.empty((P, 6), **f32) if has_cov else None
+            gin = _lib.DgrImageGrads(_ptr(gC), _ptr(gD), _ptr(gA))
+            gout = _lib.DgrGaussianGrads(_ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh), _ptr(d_col), _ptr(d_opac), _ptr(d_scales),
+                                         _ptr(d_rot), _ptr(d_cov), 0)
+            _lib.check(lib.dgr_backward(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(binning),
+                                        ctypes.c_uint64(ctx.num_rendered), _ptr(image), _ptr(radii), _ptr(alpha),
+                                        ctypes.byref(gin), ctypes.byref(gout), _stream_ptr(dev)))
+        return d_means3D, d_means2D, d_sh, d_col, d_opac, d_scales, d_rot, d_cov, None
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                     raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    """Constructed per render call by the reference (gs_renderer.py:760): construction is trivial."""
+
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            lib = _lib.load()
+            pos = _dev_f32(positions, "positions")
+            view, proj = _dev_f32(rs.viewmatrix, "viewmatrix"), _dev_f32(rs.projmatrix, "projmatrix")
+            present = torch.empty((pos.shape[0],), dtype=torch.uint8, device=pos.device)
+            with torch.cuda.device(pos.device):
+                _lib.check(lib.dgr_mark_visible(pos.shape[0], _ptr(pos), _ptr(view), _ptr(proj), _ptr(present), _stream_ptr(pos.device)))
+            return present.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   self.raster_settings)

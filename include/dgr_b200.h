@@ -1,0 +1,130 @@
+/*
+ * dgr_b200.h — C ABI of the B200-native differentiable Gaussian-splat rasterizer (libdgr_b200.so).
+ *
+ * This is the drop-in boundary for the ONE native call DreamGaussian makes on its hot path:
+ *   GaussianRasterizer(raster_settings)(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+ *   cov3D_precomp) -> (color, radii, depth, alpha)          /root/reference/gs_renderer.py:745-809
+ * The reference binds that through the pybind module `diff_gaussian_rasterization._C` of an un-vendored package
+ * (readme.md:30-32): `rasterize_gaussians`, `rasterize_gaussians_backward`, `mark_visible`  [EXT, SURVEY.md §8b].
+ * The entry points below are what those three bindings would call; everything is plain pointers and sizes, no
+ * torch types.  All pointers are DEVICE pointers unless named *_host.  All work is enqueued on `stream`
+ * (a cudaStream_t passed as void*); nothing here synchronises the device unless stated.
+ *
+ * Return value: 0 on success, otherwise a cudaError_t / negative dgr error code; dgr_last_error() has the text.
+ */
+#ifndef DGR_B200_H
+#define DGR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGR_ABI_VERSION 1
+
+/* == GaussianRasterizationSettings, the 12-field NamedTuple built at gs_renderer.py:745-758 == */
+typedef struct DgrSettings {
+    int32_t image_height;
+    int32_t image_width;
+    float   tanfovx;
+    float   tanfovy;
+    float   scale_modifier;
+    int32_t sh_degree;       /* active degree, 0..3 */
+    int32_t prefiltered;     /* accepted, unused (always False in the reference, gs_renderer.py:756) */
+    int32_t debug;           /* !=0: synchronise and check after every kernel */
+    const float *bg;         /* [3]   */
+    const float *viewmatrix; /* [4,4] row-major, p_view = [p,1] @ V   (gs_renderer.py:656-662) */
+    const float *projmatrix; /* [4,4] row-major, full projection      (gs_renderer.py:663-670) */
+    const float *campos;     /* [3]   as given by the caller (= -c2w[:3,3], gs_renderer.py:671) */
+} DgrSettings;
+
+/* == the per-Gaussian inputs of GaussianRasterizer.forward (gs_renderer.py:800-809); float32, contiguous == */
+typedef struct DgrGaussians {
+    int32_t P;                   /* number of Gaussians */
+    int32_t M;                   /* SH coefficients per channel in `shs` (= shs.shape[1]); 0 if shs == NULL */
+    const float *means3D;        /* [P,3]   */
+    const float *shs;            /* [P,M,3] or NULL (then colors_precomp) */
+    const float *colors_precomp; /* [P,3]   or NULL */
+    const float *opacities;      /* [P,1]   */
+    const float *scales;         /* [P,3]   or NULL (then cov3D_precomp) */
+    const float *rotations;      /* [P,4]   (w,x,y,z), consumed un-normalised */
+    const float *cov3D_precomp;  /* [P,6]   xx,xy,xz,yy,yz,zz or NULL */
+} DgrGaussians;
+
+/* == outputs of the forward (gs_renderer.py:800) == */
+typedef struct DgrImages {
+    float   *color;  /* [3,H,W] */
+    float   *depth;  /* [1,H,W] sum depth*alpha*T (not normalised) */
+    float   *alpha;  /* [1,H,W] sum alpha*T */
+    int32_t *radii;  /* [P]     0 = not rendered */
+} DgrImages;
+
+/* == upstream gradients into the backward; any pointer may be NULL (= zeros) == */
+typedef struct DgrImageGrads {
+    const float *dL_dcolor; /* [3,H,W] */
+    const float *dL_ddepth; /* [1,H,W] */
+    const float *dL_dalpha; /* [1,H,W] */
+} DgrImageGrads;
+
+/* == gradients w.r.t. the inputs; any pointer may be NULL (= not wanted) == */
+typedef struct DgrGaussianGrads {
+    float *dL_dmeans3D;        /* [P,3]   */
+    float *dL_dmeans2D;        /* [P,3]   NDC units, z = 0 (gs_renderer.py:626 reads [:, :2]) */
+    float *dL_dshs;            /* [P,M,3] */
+    float *dL_dcolors_precomp; /* [P,3]   */
+    float *dL_dopacities;      /* [P,1]   */
+    float *dL_dscales;         /* [P,3]   */
+    float *dL_drotations;      /* [P,4]   */
+    float *dL_dcov3D_precomp;  /* [P,6]   */
+    int32_t accumulate;        /* 0: overwrite; 1: add into the buffers (several views -> one flat gradient) */
+} DgrGaussianGrads;
+
+/* Scratch sizes.  The caller owns the three scratch buffers (upstream: geomBuffer / binningBuffer / imgBuffer),
+ * must keep them alive and untouched between a forward and its backward, and aligns them to 256 bytes. */
+size_t dgr_geom_bytes(int32_t P);
+size_t dgr_image_bytes(int32_t image_height, int32_t image_width);
+size_t dgr_binning_bytes(uint64_t capacity_instances, int32_t image_height, int32_t image_width);
+
+/* Forward, stage 1: per-Gaussian preprocess (cull, EWA cov2D, conic, radius, SH->RGB) + instance count.
+ * Writes radii.  The number of tile instances is written to geom scratch and, if n_instances_host != NULL
+ * (pinned host memory), copied there asynchronously on `stream` (uint64). */
+int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *geom, int32_t *radii,
+                           uint64_t *n_instances_host, void *stream);
+
+/* Forward, stage 2: tile binning + depth sort + per-tile front-to-back compositing.
+ * `capacity_instances` is the instance capacity `binning` was sized for; if the true count exceeds it the
+ * call renders a truncated instance list and the caller must re-run stage 2 with a larger buffer
+ * (compare *n_instances_host with the capacity after the stream has passed stage 1). */
+int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom, void *binning,
+                       uint64_t capacity_instances, void *image, const DgrImages *out, void *stream);
+
+/* Backward of both stages.  geom / binning / image are the scratch buffers of the matching forward
+ * (`capacity_instances` = the value stage 2 ran with); geom is also used as scratch for the per-Gaussian
+ * reduction.  `out_alpha` is the alpha image the forward produced (accepted for signature parity with the
+ * reference binding; the final transmittance is kept in `image` at full precision instead of 1 - alpha). */
+int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom, const void *binning,
+                 uint64_t capacity_instances, const void *image, const int32_t *radii, const float *out_alpha,
+                 const DgrImageGrads *gin, const DgrGaussianGrads *gout, void *stream);
+
+/* GaussianRasterizer.markVisible: present[i] = 1 if Gaussian i passes the near-plane test. */
+int dgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                     uint8_t *present, void *stream);
+
+/* Introspection for tests: copies per-Gaussian forward state out of geom scratch (any pointer may be NULL):
+ * mean_px [P,2], depth [P], conic [P,3] (natural units), rgb [P,3], opacity-aware pixel AABB [P,4] int32. */
+int dgr_debug_geom(int32_t P, const void *geom, float *mean_px, float *depth, float *conic, float *rgb,
+                   int32_t *aabb, uint32_t *tiles_touched, void *stream);
+
+/* How many kernels of THIS library were launched by the calling thread since the last reset (for bench.py). */
+uint64_t dgr_launch_count(void);
+void dgr_reset_launch_count(void);
+
+int dgr_abi_version(void);
+const char *dgr_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGR_B200_H */

@@ -220,7 +220,7 @@ FN(Ctx) *FN(dgr_oracle_forward)(
         REAL lam1 = mid + (REAL)sqrt((double)disc), lam2 = mid - (REAL)sqrt((double)disc);
         REAL rr = (REAL)DGR_RADIUS_SIGMAS * (REAL)sqrt((double)FN(rmax)(lam1, lam2));
         int radius = (int)ceil((double)rr);
-        if (fabs((double)rr - floor((double)rr + 0.5)) < eps * 50 * (double)rr) c->ambig_g[g] |= 4;
+        if (fabs((double)rr - floor((double)rr + 0.5)) < eps * 5 * (double)rr) c->ambig_g[g] |= 4;
         REAL mx = ((ndcx + (REAL)1) * (REAL)W - (REAL)1) * (REAL)0.5;
         REAL my = ((ndcy + (REAL)1) * (REAL)H - (REAL)1) * (REAL)0.5;
         /* tile rect (C cast = truncation toward zero, then clamp to the grid) */
@@ -229,7 +229,7 @@ FN(Ctx) *FN(dgr_oracle_forward)(
         int r4[4];
         for (int i = 0; i < 4; i++) {
             double ev = (double)e[i];
-            if (fabs(ev - floor(ev + 0.5)) < eps * 50 * (1.0 + fabs(ev))) c->ambig_g[g] |= 4;
+            if (fabs(ev - floor(ev + 0.5)) < eps * 5 * (1.0 + fabs(ev))) c->ambig_g[g] |= 4;
             int lim = (i & 1) ? gy : gx;
             int v = (ev >= 2147483000.0) ? lim : (ev <= -2147483000.0 ? 0 : (int)e[i]);
             r4[i] = v < 0 ? 0 : (v > lim ? lim : v);
@@ -295,17 +295,17 @@ FN(Ctx) *FN(dgr_oracle_forward)(
                 REAL dx = c->px[g] - (REAL)xx, dy = c->py[g] - (REAL)yy;
                 const REAL *co = c->conic + 3 * (size_t)g;
                 REAL power = (REAL)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
-                if (power > (REAL)-1e-7 && power < (REAL)1e-7) { amb = 1; c->ambig_g[g] |= 1; }
+                if (power > (REAL)-1e-7 && power < (REAL)1e-7) { amb |= 8; c->ambig_g[g] |= 1; }
                 if (power > 0) continue;
                 REAL og = c->opac[g] * (REAL)exp((double)power);
                 REAL a = FN(rmin)((REAL)DGR_ALPHA_MAX, og);
-                if (fabs((double)a - (double)DGR_ALPHA_MIN) < eps * (double)DGR_ALPHA_MIN) { amb = 1; c->ambig_g[g] |= 1; }
+                if (fabs((double)a - (double)DGR_ALPHA_MIN) < eps * (double)DGR_ALPHA_MIN) { amb |= 1; c->ambig_g[g] |= 1; }
                 if (a < (REAL)DGR_ALPHA_MIN) continue;
                 REAL test_T = T * ((REAL)1 - a);
-                if (fabs((double)test_T - (double)DGR_T_STOP) < eps * (double)DGR_T_STOP && (double)(a * T) > 1e-5) { amb = 1; c->ambig_g[g] |= 1; }
+                if (fabs((double)test_T - (double)DGR_T_STOP) < eps * (double)DGR_T_STOP && (double)(a * T) > 1e-5) { amb |= 2; c->ambig_g[g] |= 1; }
                 if (test_T < (REAL)DGR_T_STOP) break;
-                if (have_last && fabs((double)c->depth[g] - (double)last_depth) < eps * 0.05 * (double)c->depth[g]) {
-                    amb = 1; c->ambig_g[g] |= 2; c->ambig_g[last_g] |= 2; }
+                if (have_last && fabs((double)c->depth[g] - (double)last_depth) < eps * 0.03 * (double)c->depth[g]) {
+                    amb |= 4; c->ambig_g[g] |= 2; c->ambig_g[last_g] |= 2; }
                 have_last = 1; last_depth = c->depth[g]; last_g = g;
                 REAL w = a * T;
                 for (int ch = 0; ch < 3; ch++) C[ch] += c->rgb[3 * (size_t)g + ch] * w;

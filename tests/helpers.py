@@ -1,0 +1,133 @@
+"""Shared test helpers: scene construction, running the oracle and the CUDA op, parity metrics.
+
+Parity tolerances (fp32 CUDA vs float64 oracle), stated once:
+  * images (color / depth / alpha): |cuda - oracle| <= IMG_ATOL = 1e-4 (depth scaled by max(1, max|depth|)) on every
+    pixel the oracle does not flag as decision-ambiguous; flagged pixels (a float32 implementation may legitimately
+    take the other side of alpha >= 1/255, the T-stop or a depth tie) must be few and within AMBIG_ATOL;
+  * radii: exact on every Gaussian the oracle does not flag (ceil / tile-rect boundary within rounding);
+  * gradients: |cuda - oracle| <= GRAD_RTOL * |oracle| + GRAD_ATOL * max|oracle| per tensor on unflagged Gaussians.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from dreamgaussian_b200 import scene  # noqa: E402
+from oracle import c_oracle  # noqa: E402
+
+IMG_ATOL = 1e-4
+AMBIG_ATOL = 2e-2
+GRAD_RTOL = 2e-3
+GRAD_ATOL = 1e-4
+MAX_AMBIG_FRAC = 0.02
+
+
+def make_case(P, res, deg, seed=0, elev=0.0, azim=0.0, opacity="trained", sigma=None, anisotropic=True, radius=2.0,
+              bg=(1.0, 1.0, 1.0), scale_modifier=1.0, width=None, height=None):
+    cloud = scene.make_cloud(P, deg, seed=seed, opacity=opacity, sigma=sigma, anisotropic=anisotropic)
+    W = width or res
+    Hh = height or res
+    cam = scene.orbit_camera(elev, azim, radius, W, Hh)
+    settings = dict(image_height=Hh, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                    bg=np.asarray(bg, np.float32), scale_modifier=scale_modifier, viewmatrix=cam.world_view_transform,
+                    projmatrix=cam.full_proj_transform, sh_degree=deg, campos=cam.camera_center)
+    inputs = dict(means3D=cloud["means3D"], opacities=cloud["opacities"], shs=cloud["shs"], scales=cloud["scales"],
+                  rotations=cloud["rotations"])
+    return settings, inputs
+
+
+def upstream_grads(H, W, seed=123, depth=True):
+    rng = np.random.default_rng(seed)
+    gC = rng.normal(size=(3, H, W)).astype(np.float32)
+    gD = rng.normal(size=(1, H, W)).astype(np.float32) if depth else None
+    gA = rng.normal(size=(1, H, W)).astype(np.float32)
+    return gC, gD, gA
+
+
+def run_oracle(settings, inputs, grads=None, dtype=np.float64, eps=2e-5):
+    r = c_oracle.forward(**settings, **inputs, dtype=dtype, eps=eps)
+    out = dict(color=r.color, depth=r.depth, alpha=r.alpha, radii=r.radii)
+    apx, ag, n = r.flags()
+    out.update(ambig_px=apx, ambig_g=ag, n_inst=n)
+    if grads is not None:
+        out["grads"] = r.backward(*grads)
+    r.close()
+    return out
+
+
+def run_cuda(settings, inputs, grads=None, device="cuda"):
+    """The product path: GaussianRasterizer on CUDA tensors. Returns numpy outputs (+ grads)."""
+    import torch
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    t = lambda a: torch.tensor(np.asarray(a, np.float32), device=device)
+    rs = GaussianRasterizationSettings(
+        image_height=settings["image_height"], image_width=settings["image_width"], tanfovx=settings["tanfovx"],
+        tanfovy=settings["tanfovy"], bg=t(settings["bg"]), scale_modifier=settings["scale_modifier"],
+        viewmatrix=t(settings["viewmatrix"]), projmatrix=t(settings["projmatrix"]), sh_degree=settings["sh_degree"],
+        campos=t(settings["campos"]), prefiltered=False, debug=False)
+    tin = {k: t(v).requires_grad_(grads is not None) for k, v in inputs.items()}
+    means2D = torch.zeros_like(tin["means3D"], requires_grad=grads is not None)
+    color, radii, depth, alpha = GaussianRasterizer(raster_settings=rs)(means2D=means2D, **tin)
+    out = dict(color=color.detach().cpu().numpy(), depth=depth.detach().cpu().numpy(), alpha=alpha.detach().cpu().numpy(),
+               radii=radii.cpu().numpy())
+    if grads is not None:
+        gC, gD, gA = grads
+        loss = (color * t(gC)).sum() + (alpha * t(gA)).sum()
+        if gD is not None:
+            loss = loss + (depth * t(gD)).sum()
+        loss.backward()
+        g = {k: v.grad.detach().cpu().numpy() for k, v in tin.items()}
+        g["means2D"] = means2D.grad.detach().cpu().numpy()
+        out["grads"] = g
+    return out
+
+
+def compare(cu, ref, check_grads=True):
+    """Returns (ok, report dict). cu = CUDA outputs (float32), ref = oracle outputs with flags."""
+    rep = {}
+    ok = True
+    apx = ref["ambig_px"].astype(bool)
+    ag = ref["ambig_g"]
+    rep["ambig_px_frac"] = float(apx.mean()) if apx.size else 0.0
+    rep["ambig_g_frac"] = float((ag != 0).mean()) if ag.size else 0.0
+    if rep["ambig_px_frac"] > MAX_AMBIG_FRAC:
+        ok = False
+    for name in ("color", "depth", "alpha"):
+        d = np.abs(cu[name].astype(np.float64) - ref[name])
+        scale = max(1.0, float(np.abs(ref[name]).max())) if name == "depth" else 1.0
+        m = np.broadcast_to(apx[None], d.shape)
+        clean = d[~m].max() if (~m).any() else 0.0
+        amb = d[m].max() if m.any() else 0.0
+        rep[name + "_err"] = float(clean / scale)
+        rep[name + "_err_ambig"] = float(amb / scale)
+        if clean / scale > IMG_ATOL or amb / scale > AMBIG_ATOL:
+            ok = False
+    rad_bad = (cu["radii"] != ref["radii"]) & ((ag & 4) == 0)
+    rep["radii_mismatch"] = int(rad_bad.sum())
+    rep["radii_mismatch_flagged"] = int(((cu["radii"] != ref["radii"]) & ((ag & 4) != 0)).sum())
+    if rad_bad.any():
+        ok = False
+    if check_grads and "grads" in ref:
+        clean_g = ag == 0
+        # a tensor whose true gradient vanishes by symmetry (e.g. rotations of isotropic Gaussians) is judged
+        # against the scale of the other gradients, not against its own round-off
+        floor = 1e-3 * max(float(np.abs(v).max()) if v.size else 0.0 for v in ref["grads"].values())
+        for k, gr in ref["grads"].items():
+            if k not in cu["grads"]:
+                continue
+            gc = cu["grads"][k].astype(np.float64).reshape(gr.shape)
+            scale = max(float(np.abs(gr).max()) if gr.size else 0.0, floor) or 1.0
+            err = np.abs(gc - gr) - GRAD_RTOL * np.abs(gr)
+            e2 = err.reshape(gr.shape[0], -1).max(axis=1) if gr.shape[0] else np.zeros(0)
+            worst = float(e2[clean_g].max() / scale) if clean_g.any() else 0.0
+            worst_amb = float(e2[~clean_g].max() / scale) if (~clean_g).any() else 0.0
+            rep["grad_" + k] = worst
+            rep["grad_" + k + "_ambig"] = worst_amb
+            rep["grad_" + k + "_scale"] = scale
+            if worst > GRAD_ATOL or worst_amb > 0.05:
+                ok = False
+    return ok, rep

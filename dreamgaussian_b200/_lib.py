@@ -48,6 +48,7 @@ EXPORTS = (
     "dgr_abi_version", "dgr_last_error", "dgr_launch_count", "dgr_reset_launch_count",
     "dgr_geom_bytes", "dgr_image_bytes", "dgr_binning_bytes",
     "dgr_forward_preprocess", "dgr_forward_render", "dgr_backward", "dgr_mark_visible", "dgr_debug_geom",
+    "dgr_profile_enable", "dgr_profile_collect",
 )
 
 _lib = None
@@ -95,10 +96,24 @@ def load():
     lib.dgr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
     lib.dgr_debug_geom.restype = ctypes.c_int
     lib.dgr_debug_geom.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.dgr_profile_enable.restype = None
+    lib.dgr_profile_enable.argtypes = [ctypes.c_int]
+    lib.dgr_profile_collect.restype = ctypes.c_int
+    lib.dgr_profile_collect.argtypes = [ctypes.c_char_p, ctypes.c_size_t, vp, ctypes.c_int]
     if lib.dgr_abi_version() != 1:
         raise RuntimeError("libdgr_b200.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+def profile_collect(max_records=4096):
+    """-> list of (kernel name, milliseconds) recorded since dgr_profile_enable(1)."""
+    lib = load()
+    names = ctypes.create_string_buffer(64 * max_records)
+    ms = (ctypes.c_float * max_records)()
+    n = lib.dgr_profile_collect(names, len(names), ctypes.cast(ms, ctypes.c_void_p), max_records)
+    nm = names.value.decode().split("\n")[:n]
+    return list(zip(nm, [float(ms[i]) for i in range(n)]))
 
 
 def check(code):

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/dgr_b200.h"
 #include "dgr_backward.cuh"
@@ -31,6 +32,29 @@ int fail(int code, const char *what, const char *detail = nullptr) {
         cudaError_t e_ = (call);                                                               \
         if (e_ != cudaSuccess) return fail((int)e_, #call, cudaGetErrorString(e_));            \
     } while (0)
+// optional per-kernel CUDA-event timing (bench.py's live roofline): events bracket every launch on its stream
+struct ProfRec { const char *name; cudaEvent_t a, b; };
+thread_local bool g_prof_on = false;
+thread_local std::vector<ProfRec> g_prof;
+inline void prof_begin(const char *name, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfRec r; r.name = name;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+}
+inline void prof_end(cudaStream_t st) {
+    if (!g_prof_on) return;
+    cudaEventRecord(g_prof.back().b, st);
+}
+#define DGR_KERNEL(name, st, dbg, ...)          \
+    do {                                         \
+        prof_begin(name, st);                    \
+        __VA_ARGS__;                             \
+        prof_end(st);                            \
+        DGR_LAUNCHED(st, dbg);                   \
+    } while (0)
+
 #define DGR_LAUNCHED(s, dbg)                                                                   \
     do {                                                                                       \
         g_launches++;                                                                          \
@@ -119,6 +143,29 @@ __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched
 extern "C" {
 
 int dgr_abi_version(void) { return DGR_ABI_VERSION; }
+
+void dgr_profile_enable(int on) {
+    for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = on != 0;
+}
+// Synchronises the recorded events; writes up to `max` (name, milliseconds) pairs, names as a '\n'-joined string.
+int dgr_profile_collect(char *names, size_t names_bytes, float *ms, int max) {
+    int n = 0; size_t off = 0;
+    if (names && names_bytes) names[0] = 0;
+    for (auto &r : g_prof) {
+        if (n >= max) break;
+        if (cudaEventSynchronize(r.b) != cudaSuccess) break;
+        float t = 0.f; cudaEventElapsedTime(&t, r.a, r.b);
+        ms[n] = t;
+        size_t L = strlen(r.name);
+        if (names && off + L + 2 < names_bytes) { memcpy(names + off, r.name, L); off += L; names[off++] = '\n'; names[off] = 0; }
+        n++;
+    }
+    for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    return n;
+}
 const char *dgr_last_error(void) { return g_err.c_str(); }
 uint64_t dgr_launch_count(void) { return g_launches; }
 void dgr_reset_launch_count(void) { g_launches = 0; }
@@ -143,6 +190,7 @@ int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *ge
     if (g->P > 0) {
         if (!radii) return fail(-1, "radii is NULL");
         const bool sh = g->shs != nullptr, cov = g->cov3D_precomp != nullptr;
+        prof_begin("preprocess_fwd", st);
         if (sh) {
 #define DGR_DISPATCH_DEG(D)                                                     \
     case D:                                                                     \
@@ -155,6 +203,7 @@ int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *ge
             if (cov) launch_pre_fwd<0, false, true>(s, g, radii, geom, L, st);
             else launch_pre_fwd<0, false, false>(s, g, radii, geom, L, st);
         }
+        prof_end(st);
         DGR_LAUNCHED(st, s->debug);
     }
     if (n_instances_host)
@@ -194,22 +243,30 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
         unsigned *vals_alt = reinterpret_cast<unsigned *>(binning + BL.off_vals_alt);
         Rec *recs = reinterpret_cast<Rec *>(binning + BL.off_rec);
         const Rec *rec = reinterpret_cast<const Rec *>(geom + GL.off_rec);
+        prof_begin("emit_instances", st);
         emit_instances_kernel<<<(g->P + 255) / 256, 256, 0, st>>>(
             g->P, IL.gx, rec, reinterpret_cast<const unsigned *>(geom + GL.off_offsets),
             reinterpret_cast<const unsigned *>(geom + GL.off_touched), capacity, keys, vals);
+        prof_end(st);
         DGR_LAUNCHED(st, s->debug);
         int tile_bits = 0;
         while (((size_t)1 << tile_bits) < tiles) tile_bits++;
         size_t tb = temp_bytes;
+        prof_begin("radix_sort(cub)", st);
         DGR_CUDA(cub::DeviceRadixSort::SortPairs(binning + BL.off_temp, tb, keys, keys_alt, vals, vals_alt, (int)n, 0, 32 + tile_bits, st));
+        prof_end(st);
         g_launches += 1;   // counted as one library step (CUB launches several kernels internally)
+        prof_begin("ranges_gather", st);
         ranges_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, keys_alt, vals_alt, rec, ranges, recs);
+        prof_end(st);
         DGR_LAUNCHED(st, s->debug);
         rec_sorted = recs;
     }
     float *final_T = reinterpret_cast<float *>(image + IL.total);
+    prof_begin("render_fwd", st);
     render_fwd_kernel<<<(unsigned)tiles, kTileThreads, 0, st>>>(H, W, IL.gx, ranges, rec_sorted, s->bg, out->color, out->depth,
                                                                out->alpha, n_contrib, final_T);
+    prof_end(st);
     DGR_LAUNCHED(st, s->debug);
     return 0;
 }
@@ -238,12 +295,15 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
         const unsigned *ids_sorted = reinterpret_cast<const unsigned *>(binning + BL.off_vals_alt);
         const Rec *recs = reinterpret_cast<const Rec *>(binning + BL.off_rec);
         const float *final_T = reinterpret_cast<const float *>(image + IL.total);
+        prof_begin("render_bwd", st);
         render_bwd_kernel<<<(unsigned)tiles, kTileThreads, 0, st>>>(
             H, W, IL.gx, reinterpret_cast<const uint2 *>(image + IL.off_ranges), recs, ids_sorted, s->bg, final_T,
             reinterpret_cast<const unsigned *>(image + IL.off_ncontrib), gin->dL_dcolor, gin->dL_ddepth, gin->dL_dalpha, grad_rec);
+        prof_end(st);
         DGR_LAUNCHED(st, s->debug);
     }
     const bool sh = g->shs != nullptr, cov = g->cov3D_precomp != nullptr;
+    prof_begin("preprocess_bwd", st);
     if (sh) {
 #define DGR_DISPATCH_DEG(D)                                                       \
     case D:                                                                       \
@@ -256,6 +316,7 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
         if (cov) launch_pre_bwd<0, false, true>(s, g, radii, grad_rec, gout, st);
         else launch_pre_bwd<0, false, false>(s, g, radii, grad_rec, gout, st);
     }
+    prof_end(st);
     DGR_LAUNCHED(st, s->debug);
     return 0;
 }

@@ -94,81 +94,105 @@ def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class ForwardState:
+    """Everything one forward leaves behind for its backward (upstream: ctx + geom/binning/img buffers)."""
+    __slots__ = ("rs", "frame", "num_rendered", "geom", "binning", "image", "radii", "alpha", "tensors")
+
+
+def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D):
+    """Runs both forward stages through the C ABI. Inputs are validated CUDA float32 tensors (or None).
+    Returns (color, radii, depth, alpha, ForwardState)."""
+    lib = _lib.load()
+    dev = means3D.device
+    with torch.cuda.device(dev):
+        fr = _Frame(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D)
+        H, W, P = int(rs.image_height), int(rs.image_width), fr.P
+        u8 = dict(dtype=torch.uint8, device=dev)
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        alpha = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        geom = torch.empty((lib.dgr_geom_bytes(P),), **u8)
+        image = torch.empty((lib.dgr_image_bytes(H, W),), **u8)
+        n_host = _pinned_counter()
+        st = _stream_ptr(dev)
+        _lib.check(lib.dgr_forward_preprocess(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(radii),
+                                              ctypes.c_void_p(n_host.data_ptr()), st))
+        torch.cuda.current_stream(dev).synchronize()
+        n_inst = int(n_host[0])
+        binning = torch.empty((lib.dgr_binning_bytes(n_inst, H, W),), **u8) if n_inst > 0 else None
+        out = _lib.DgrImages(_ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii))
+        _lib.check(lib.dgr_forward_render(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(binning),
+                                          ctypes.c_uint64(n_inst), _ptr(image), ctypes.byref(out), st))
+    state = ForwardState()
+    state.rs, state.frame, state.num_rendered = rs, fr, n_inst
+    state.geom, state.binning, state.image, state.radii, state.alpha = geom, binning, image, radii, alpha
+    state.tensors = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3D)
+    return color, radii, depth, alpha, state
+
+
+_PINNED = {}
+
+
+def _pinned_counter():
+    """One pinned uint64 per host thread for the instance-count read-back."""
+    import threading
+    key = threading.get_ident()
+    t = _PINNED.get(key)
+    if t is None:
+        t = torch.zeros((1,), dtype=torch.int64).pin_memory()
+        _PINNED[key] = t
+    return t
+
+
+def backward_impl(state, grad_color, grad_depth, grad_alpha, d_means3D, d_means2D, d_sh, d_col, d_opac, d_scales, d_rot,
+                  d_cov, accumulate=False):
+    """Runs the backward through the C ABI, writing (or accumulating) into the given gradient tensors."""
+    lib = _lib.load()
+    fr = state.frame
+    dev = state.radii.device
+    with torch.cuda.device(dev):
+        gin = _lib.DgrImageGrads(_ptr(grad_color), _ptr(grad_depth), _ptr(grad_alpha))
+        gout = _lib.DgrGaussianGrads(_ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh), _ptr(d_col), _ptr(d_opac), _ptr(d_scales),
+                                     _ptr(d_rot), _ptr(d_cov), 1 if accumulate else 0)
+        _lib.check(lib.dgr_backward(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(state.geom), _ptr(state.binning),
+                                    ctypes.c_uint64(state.num_rendered), _ptr(state.image), _ptr(state.radii), _ptr(state.alpha),
+                                    ctypes.byref(gin), ctypes.byref(gout), _stream_ptr(dev)))
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
-        lib = _lib.load()
-        rs = raster_settings
         means3D = _dev_f32(means3D, "means3D")
         opacities = _dev_f32(opacities, "opacities")
         sh, colors_precomp = _opt(sh, "shs"), _opt(colors_precomp, "colors_precomp")
         scales, rotations, cov3D = _opt(scales, "scales"), _opt(rotations, "rotations"), _opt(cov3Ds_precomp, "cov3D_precomp")
-        dev = means3D.device
-        with torch.cuda.device(dev):
-            fr = _Frame(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D)
-            H, W, P = int(rs.image_height), int(rs.image_width), fr.P
-            u8 = dict(dtype=torch.uint8, device=dev)
-            color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
-            depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
-            alpha = torch.empty((1, H, W), dtype=torch.float32, device=dev)
-            radii = torch.empty((P,), dtype=torch.int32, device=dev)
-            geom = torch.empty((lib.dgr_geom_bytes(P),), **u8)
-            image = torch.empty((lib.dgr_image_bytes(H, W),), **u8)
-            n_host = torch.zeros((1,), dtype=torch.int64).pin_memory()
-            st = _stream_ptr(dev)
-            _lib.check(lib.dgr_forward_preprocess(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(radii),
-                                                  ctypes.c_void_p(n_host.data_ptr()), st))
-            torch.cuda.current_stream(dev).synchronize()
-            n_inst = int(n_host.item())
-            binning = torch.empty((lib.dgr_binning_bytes(n_inst, H, W),), **u8) if n_inst > 0 else None
-            out = _lib.DgrImages(_ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii))
-            _lib.check(lib.dgr_forward_render(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(binning),
-                                              ctypes.c_uint64(n_inst), _ptr(image), ctypes.byref(out), st))
-        ctx.raster_settings = rs
-        ctx.num_rendered = n_inst
-        ctx.has = (sh is not None, colors_precomp is not None, scales is not None, cov3D is not None)
-        ctx.scratch = (geom, binning, image)
-        none = means3D.new_empty(0)
-        ctx.save_for_backward(means3D, sh if sh is not None else none, colors_precomp if colors_precomp is not None else none,
-                              opacities, scales if scales is not None else none, rotations if rotations is not None else none,
-                              cov3D if cov3D is not None else none, radii, alpha)
+        color, radii, depth, alpha, state = forward_impl(raster_settings, means3D, sh, colors_precomp, opacities, scales,
+                                                         rotations, cov3D)
+        ctx.state = state
         ctx.mark_non_differentiable(radii)
         return color, radii, depth, alpha
 
     @staticmethod
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
-        lib = _lib.load()
-        rs = ctx.raster_settings
-        means3D, sh, colors_precomp, opacities, scales, rotations, cov3D, radii, alpha = ctx.saved_tensors
-        has_sh, has_col, has_scale, has_cov = ctx.has
-        sh = sh if has_sh else None
-        colors_precomp = colors_precomp if has_col else None
-        scales = scales if has_scale else None
-        rotations = rotations if has_scale else None
-        cov3D = cov3D if has_cov else None
-        geom, binning, image = ctx.scratch
+        state = ctx.state
+        means3D, sh, colors_precomp, opacities, scales, rotations, cov3D = state.tensors
         dev = means3D.device
-        with torch.cuda.device(dev):
-            fr = _Frame(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D)
-            P, M = fr.P, fr.M
-            f32 = dict(dtype=torch.float32, device=dev)
-            gC = _dev_f32(grad_color, "grad_color") if grad_color is not None else None
-            gD = _dev_f32(grad_depth, "grad_depth") if grad_depth is not None else None
-            gA = _dev_f32(grad_alpha, "grad_alpha") if grad_alpha is not None else None
-            d_means3D = torch.empty((P, 3), **f32)
-            d_means2D = torch.empty((P, 3), **f32)
-            d_opac = torch.empty((P, 1), **f32)
-            d_sh = torch.empty((P, M, 3), **f32) if has_sh else None
-            d_col = torch.empty((P, 3), **f32) if has_col else None
-            d_scales = torch.empty((P, 3), **f32) if has_scale else None
-            d_rot = torch.empty((P, 4), **f32) if has_scale else None
-            d_cov = torch.empty((P, 6), **f32) if has_cov else None
-            gin = _lib.DgrImageGrads(_ptr(gC), _ptr(gD), _ptr(gA))
-            gout = _lib.DgrGaussianGrads(_ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh), _ptr(d_col), _ptr(d_opac), _ptr(d_scales),
-                                         _ptr(d_rot), _ptr(d_cov), 0)
-            _lib.check(lib.dgr_backward(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(binning),
-                                        ctypes.c_uint64(ctx.num_rendered), _ptr(image), _ptr(radii), _ptr(alpha),
-                                        ctypes.byref(gin), ctypes.byref(gout), _stream_ptr(dev)))
+        P, M = state.frame.P, state.frame.M
+        f32 = dict(dtype=torch.float32, device=dev)
+        gC = _dev_f32(grad_color, "grad_color") if grad_color is not None else None
+        gD = _dev_f32(grad_depth, "grad_depth") if grad_depth is not None else None
+        gA = _dev_f32(grad_alpha, "grad_alpha") if grad_alpha is not None else None
+        d_means3D = torch.empty((P, 3), **f32)
+        d_means2D = torch.empty((P, 3), **f32)
+        d_opac = torch.empty((P, 1), **f32)
+        d_sh = torch.empty((P, M, 3), **f32) if sh is not None else None
+        d_col = torch.empty((P, 3), **f32) if colors_precomp is not None else None
+        d_scales = torch.empty((P, 3), **f32) if scales is not None else None
+        d_rot = torch.empty((P, 4), **f32) if rotations is not None else None
+        d_cov = torch.empty((P, 6), **f32) if cov3D is not None else None
+        backward_impl(state, gC, gD, gA, d_means3D, d_means2D, d_sh, d_col, d_opac, d_scales, d_rot, d_cov)
+        ctx.state = None
         return d_means3D, d_means2D, d_sh, d_col, d_opac, d_scales, d_rot, d_cov, None
 
 

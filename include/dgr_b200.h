@@ -121,6 +121,11 @@ int dgr_debug_geom(int32_t P, const void *geom, float *mean_px, float *depth, fl
 uint64_t dgr_launch_count(void);
 void dgr_reset_launch_count(void);
 
+/* Per-kernel CUDA-event timing (tracing hook): when enabled, every kernel this thread launches is bracketed by
+ * events on its stream; dgr_profile_collect waits for them and returns (name, ms) pairs, names '\n'-joined. */
+void dgr_profile_enable(int on);
+int dgr_profile_collect(char *names, size_t names_bytes, float *ms, int max);
+
 int dgr_abi_version(void);
 const char *dgr_last_error(void);
 

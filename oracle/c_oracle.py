@@ -79,7 +79,7 @@ class OracleResult:
         s = slice(0, self.P)
         return dict(px=px[s], py=py[s], depth=dep[s], conic=conic[s], rgb=rgb[s], rect=rect[s])
 
-    def backward(self, dL_dcolor=None, dL_ddepth=None, dL_dalpha=None):
+    def backward(self, dL_dcolor=None, dL_ddepth=None, dL_dalpha=None, want_moments=False):
         dt, P, M = self._dt, self.P, self.M
         cv = lambda a: None if a is None else np.ascontiguousarray(np.asarray(a, dtype=dt))
         gC, gD, gA = cv(dL_dcolor), cv(dL_ddepth), cv(dL_dalpha)
@@ -88,11 +88,16 @@ class OracleResult:
             means3D=np.zeros((Pn, 3), dt), means2D=np.zeros((Pn, 3), dt), shs=np.zeros((Pn, max(M, 1), 3), dt),
             colors_precomp=np.zeros((Pn, 3), dt), opacities=np.zeros((Pn, 1), dt), scales=np.zeros((Pn, 3), dt),
             rotations=np.zeros((Pn, 4), dt), cov3D_precomp=np.zeros((Pn, 6), dt))
+        moments = np.zeros((Pn, 10), np.float64) if want_moments else None
         getattr(lib(), "dgr_oracle_backward_" + self._suf)(
             ctypes.c_void_p(self._ctx), _ptr(gC), _ptr(gD), _ptr(gA),
             _ptr(out["means3D"]), _ptr(out["means2D"]), _ptr(out["shs"]), _ptr(out["colors_precomp"]),
-            _ptr(out["opacities"]), _ptr(out["scales"]), _ptr(out["rotations"]), _ptr(out["cov3D_precomp"]))
-        return {k: v[:P] for k, v in out.items()}
+            _ptr(out["opacities"]), _ptr(out["scales"]), _ptr(out["rotations"]), _ptr(out["cov3D_precomp"]),
+            _ptr(moments))
+        res = {k: v[:P] for k, v in out.items()}
+        if want_moments:
+            res["_moments"] = moments[:P]
+        return res
 
     def close(self):
         if self._ctx:

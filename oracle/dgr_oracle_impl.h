@@ -220,7 +220,7 @@ FN(Ctx) *FN(dgr_oracle_forward)(
         REAL lam1 = mid + (REAL)sqrt((double)disc), lam2 = mid - (REAL)sqrt((double)disc);
         REAL rr = (REAL)DGR_RADIUS_SIGMAS * (REAL)sqrt((double)FN(rmax)(lam1, lam2));
         int radius = (int)ceil((double)rr);
-        if (fabs((double)rr - floor((double)rr + 0.5)) < eps * 5 * (double)rr) c->ambig_g[g] |= 4;
+        if (fabs((double)rr - floor((double)rr + 0.5)) < 1e-4 * (double)rr) c->ambig_g[g] |= 4;
         REAL mx = ((ndcx + (REAL)1) * (REAL)W - (REAL)1) * (REAL)0.5;
         REAL my = ((ndcy + (REAL)1) * (REAL)H - (REAL)1) * (REAL)0.5;
         /* tile rect (C cast = truncation toward zero, then clamp to the grid) */
@@ -229,7 +229,7 @@ FN(Ctx) *FN(dgr_oracle_forward)(
         int r4[4];
         for (int i = 0; i < 4; i++) {
             double ev = (double)e[i];
-            if (fabs(ev - floor(ev + 0.5)) < eps * 5 * (1.0 + fabs(ev))) c->ambig_g[g] |= 4;
+            if (fabs(ev - floor(ev + 0.5)) < 1e-4 * (1.0 + fabs(ev))) c->ambig_g[g] |= 4;
             int lim = (i & 1) ? gy : gx;
             int v = (ev >= 2147483000.0) ? lim : (ev <= -2147483000.0 ? 0 : (int)e[i]);
             r4[i] = v < 0 ? 0 : (v > lim ? lim : v);
@@ -299,12 +299,16 @@ FN(Ctx) *FN(dgr_oracle_forward)(
                 if (power > 0) continue;
                 REAL og = c->opac[g] * (REAL)exp((double)power);
                 REAL a = FN(rmin)((REAL)DGR_ALPHA_MAX, og);
-                if (fabs((double)a - (double)DGR_ALPHA_MIN) < eps * (double)DGR_ALPHA_MIN) { amb |= 1; c->ambig_g[g] |= 1; }
+                /* a float32 conic carries ~1e-6 relative error and the three terms of the quadratic form cancel, so the
+                   error of `power` (= relative error of alpha) scales with the magnitude of those terms */
+                double mag = 0.5 * (fabs((double)co[0]) * (double)dx * (double)dx + fabs((double)co[2]) * (double)dy * (double)dy)
+                           + fabs((double)co[1] * (double)dx * (double)dy);
+                if (fabs((double)a - (double)DGR_ALPHA_MIN) < eps * (1.0 + mag) * (double)DGR_ALPHA_MIN) { amb |= 1; c->ambig_g[g] |= 1; }
                 if (a < (REAL)DGR_ALPHA_MIN) continue;
                 REAL test_T = T * ((REAL)1 - a);
                 if (fabs((double)test_T - (double)DGR_T_STOP) < eps * (double)DGR_T_STOP && (double)(a * T) > 1e-5) { amb |= 2; c->ambig_g[g] |= 1; }
                 if (test_T < (REAL)DGR_T_STOP) break;
-                if (have_last && fabs((double)c->depth[g] - (double)last_depth) < eps * 0.03 * (double)c->depth[g]) {
+                if (have_last && fabs((double)c->depth[g] - (double)last_depth) < 1e-6 * (double)c->depth[g]) {   /* ~8 float32 ulps */
                     amb |= 4; c->ambig_g[g] |= 2; c->ambig_g[last_g] |= 2; }
                 have_last = 1; last_depth = c->depth[g]; last_g = g;
                 REAL w = a * T;
@@ -342,7 +346,7 @@ void FN(dgr_oracle_get_state)(const FN(Ctx) *c, REAL *px, REAL *py, REAL *depth,
 void FN(dgr_oracle_backward)(
     const FN(Ctx) *c, const REAL *gC, const REAL *gD, const REAL *gA,
     REAL *dL_dmeans3D, REAL *dL_dmeans2D, REAL *dL_dshs, REAL *dL_dcolors, REAL *dL_dopacity,
-    REAL *dL_dscales, REAL *dL_drotations, REAL *dL_dcov3D)
+    REAL *dL_dscales, REAL *dL_drotations, REAL *dL_dcov3D, double *moments_out /* [P*10] or NULL: the 10 per-Gaussian sums */)
 {
     const int P = c->P, H = c->H, W = c->W, gx = c->gx, gy = c->gy, M = c->M, D = c->D;
     const size_t HW = (size_t)H * W;
@@ -414,6 +418,7 @@ void FN(dgr_oracle_backward)(
         for (size_t i = 0; i < (size_t)P * 10; i++) acc[i] += A[i];
     }
 
+    if (moments_out) memcpy(moments_out, acc, (size_t)P * 10 * sizeof(double));
     /* ---------------- A6: per-Gaussian chain rule back to the inputs ---------------- */
     const REAL *V = c->V, *PM = c->PM;
     const REAL limx = (REAL)DGR_FOV_CLAMP * c->tanfovx, limy = (REAL)DGR_FOV_CLAMP * c->tanfovy;

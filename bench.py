@@ -57,10 +57,10 @@ def kernel_algorithmic_bytes(name, P, M, H, W, n_inst):
     """Per-kernel algorithmic bytes (what the kernel must read + write once), DESIGN.md §Kernels."""
     px = H * W
     table = {
-        "preprocess_fwd": P * (44 + 12 * M) + P * (4 + 48 + 8),             # inputs; radii + record + offsets/touched
-        "emit_instances": P * 56 + n_inst * 12,                             # record + offset; key + id
-        "radix_sort(cub)": n_inst * 24,                                      # one ideal pass: read + write key+id
-        "ranges_gather": n_inst * (12 + 48 + 48),                            # key+id, record gather, sorted record
+        "preprocess_fwd": P * (44 + 12 * M) + P * (4 + 48 + 4) + n_inst * 4, # inputs; radii + record + touched; histogram
+        "tile_scan": (H // 16 + 1) * (W // 16 + 1) * 16,                    # counts in; ranges + cursor out
+        "emit_instances": P * 52 + n_inst * 12,                             # record + touched; cursor atomics + key
+        "tile_sort_gather": n_inst * (8 + 4 + 48 + 48),                     # key in; id out; record gather + sorted record
         "render_fwd": n_inst * 48 + px * 28,                                 # sorted records; rgb+depth+alpha+n_contrib+T
         "render_bwd": n_inst * 52 + px * 28 + P * 48,                        # records+ids; grads+n_contrib+T; moments
         "preprocess_bwd": P * (44 + 12 * M) + P * 52 + P * (56 + 12 * M),   # inputs; moments+radii; grads
@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -215,14 +215,15 @@ def run_ours(a, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # nvidia-smi samples every 20 ms; it is started before the warm-up so that even a short timed region is covered
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for i in range(a.warmup):
         step(i)
     barrier()
     n_inst = 0
     # ---------------- timed region: K steps, device-resident inputs, L2 flushed between steps ----------------
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     lib.dgr_reset_launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     barrier()

@@ -48,7 +48,7 @@ EXPORTS = (
     "dgr_abi_version", "dgr_last_error", "dgr_launch_count", "dgr_reset_launch_count",
     "dgr_geom_bytes", "dgr_image_bytes", "dgr_binning_bytes",
     "dgr_forward_preprocess", "dgr_forward_render", "dgr_backward", "dgr_mark_visible", "dgr_debug_geom",
-    "dgr_profile_enable", "dgr_profile_collect",
+    "dgr_profile_enable", "dgr_profile_collect", "dgr_event_create", "dgr_event_synchronize", "dgr_event_destroy", "dgr_set_tuning",
 )
 
 _lib = None
@@ -79,23 +79,30 @@ def load():
     lib.dgr_launch_count.restype = u64
     lib.dgr_reset_launch_count.restype = None
     lib.dgr_geom_bytes.restype = ctypes.c_size_t
-    lib.dgr_geom_bytes.argtypes = [i32]
+    lib.dgr_geom_bytes.argtypes = [i32, i32, i32]
     lib.dgr_image_bytes.restype = ctypes.c_size_t
     lib.dgr_image_bytes.argtypes = [i32, i32]
     lib.dgr_binning_bytes.restype = ctypes.c_size_t
     lib.dgr_binning_bytes.argtypes = [u64, i32, i32]
     lib.dgr_forward_preprocess.restype = ctypes.c_int
     lib.dgr_forward_preprocess.argtypes = [ctypes.POINTER(DgrSettings), ctypes.POINTER(DgrGaussians), vp, vp, vp, vp]
+    lib.dgr_set_tuning.restype = ctypes.c_int
+    lib.dgr_set_tuning.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.dgr_event_create.restype = vp
+    lib.dgr_event_synchronize.restype = ctypes.c_int
+    lib.dgr_event_synchronize.argtypes = [vp]
+    lib.dgr_event_destroy.restype = None
+    lib.dgr_event_destroy.argtypes = [vp]
     lib.dgr_forward_render.restype = ctypes.c_int
     lib.dgr_forward_render.argtypes = [ctypes.POINTER(DgrSettings), ctypes.POINTER(DgrGaussians), vp, vp, u64, vp,
-                                       ctypes.POINTER(DgrImages), vp]
+                                       ctypes.POINTER(DgrImages), vp, vp, vp]
     lib.dgr_backward.restype = ctypes.c_int
     lib.dgr_backward.argtypes = [ctypes.POINTER(DgrSettings), ctypes.POINTER(DgrGaussians), vp, vp, u64, vp, vp, vp,
                                  ctypes.POINTER(DgrImageGrads), ctypes.POINTER(DgrGaussianGrads), vp]
     lib.dgr_mark_visible.restype = ctypes.c_int
     lib.dgr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
     lib.dgr_debug_geom.restype = ctypes.c_int
-    lib.dgr_debug_geom.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.dgr_debug_geom.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.dgr_profile_enable.restype = None
     lib.dgr_profile_enable.argtypes = [ctypes.c_int]
     lib.dgr_profile_collect.restype = ctypes.c_int
@@ -103,6 +110,10 @@ def load():
     if lib.dgr_abi_version() != 1:
         raise RuntimeError("libdgr_b200.so ABI version mismatch")
     _lib = lib
+    tune = os.environ.get("DGR_TUNING")        # "ppl_fwd,ppl_bwd,tile_order" for experiments
+    if tune:
+        a, b, c = (int(x) for x in tune.split(","))
+        check(lib.dgr_set_tuning(a, b, c))
     return lib
 
 

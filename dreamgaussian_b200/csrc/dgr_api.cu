@@ -1,8 +1,7 @@
 // dgr_api.cu — C ABI of libdgr_b200.so (see include/dgr_b200.h).  Host-side glue only: argument checks, scratch
-// layout, kernel launches on the caller's stream.  No torch, no CPU fallback: without a CUDA device every compute
-// entry point fails with an error string.
+// layout, kernel launches on the caller's stream.  No torch, no library kernels (no CUB/cuBLAS), no CPU fallback:
+// without a CUDA device every compute entry point fails with an error string.
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 
 #include <cstdio>
 #include <cstring>
@@ -27,11 +26,7 @@ int fail(int code, const char *what, const char *detail = nullptr) {
     if (detail) { g_err += ": "; g_err += detail; }
     return code;
 }
-#define DGR_CUDA(call)                                                                         \
-    do {                                                                                       \
-        cudaError_t e_ = (call);                                                               \
-        if (e_ != cudaSuccess) return fail((int)e_, #call, cudaGetErrorString(e_));            \
-    } while (0)
+
 // optional per-kernel CUDA-event timing (bench.py's live roofline): events bracket every launch on its stream
 struct ProfRec { const char *name; cudaEvent_t a, b; };
 thread_local bool g_prof_on = false;
@@ -47,21 +42,23 @@ inline void prof_end(cudaStream_t st) {
     if (!g_prof_on) return;
     cudaEventRecord(g_prof.back().b, st);
 }
-#define DGR_KERNEL(name, st, dbg, ...)          \
-    do {                                         \
-        prof_begin(name, st);                    \
-        __VA_ARGS__;                             \
-        prof_end(st);                            \
-        DGR_LAUNCHED(st, dbg);                   \
-    } while (0)
 
-#define DGR_LAUNCHED(s, dbg)                                                                   \
+#define DGR_CUDA(call)                                                                         \
     do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) return fail((int)e_, #call, cudaGetErrorString(e_));            \
+    } while (0)
+// launch a kernel (the statement in __VA_ARGS__), count it, time it when profiling, check it
+#define DGR_KERNEL(name, st, dbg, ...)                                                         \
+    do {                                                                                       \
+        prof_begin(name, st);                                                                  \
+        __VA_ARGS__;                                                                           \
+        prof_end(st);                                                                          \
         g_launches++;                                                                          \
         cudaError_t e_ = cudaGetLastError();                                                   \
-        if (e_ != cudaSuccess) return fail((int)e_, "kernel launch", cudaGetErrorString(e_));  \
-        if (dbg) { e_ = cudaStreamSynchronize(s);                                              \
-            if (e_ != cudaSuccess) return fail((int)e_, "kernel execution", cudaGetErrorString(e_)); } \
+        if (e_ != cudaSuccess) return fail((int)e_, name, cudaGetErrorString(e_));             \
+        if (dbg) { e_ = cudaStreamSynchronize(st);                                             \
+            if (e_ != cudaSuccess) return fail((int)e_, name, cudaGetErrorString(e_)); }       \
     } while (0)
 
 int check_settings(const DgrSettings *s) {
@@ -77,11 +74,9 @@ int check_gaussians(const DgrSettings *s, const DgrGaussians *g) {
     if (g->P < 0) return fail(-1, "P < 0");
     if ((g->shs == nullptr) == (g->colors_precomp == nullptr))
         return fail(-2, "Please provide excatly one of either SHs or precomputed colors!");
-    const bool sr = g->scales != nullptr && g->rotations != nullptr;
     if (((g->scales == nullptr || g->rotations == nullptr) && g->cov3D_precomp == nullptr) ||
         ((g->scales != nullptr || g->rotations != nullptr) && g->cov3D_precomp != nullptr))
         return fail(-2, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
-    (void)sr;
     if (g->P > 0 && (!g->means3D || !g->opacities)) return fail(-1, "means3D / opacities must not be NULL");
     if (g->shs) {
         if (!s->campos) return fail(-1, "campos must not be NULL with SHs");
@@ -92,24 +87,18 @@ int check_gaussians(const DgrSettings *s, const DgrGaussians *g) {
     return 0;
 }
 
-size_t sort_temp_bytes(uint64_t cap) {
-    size_t bytes = 0;
-    unsigned long long *k = nullptr; unsigned *v = nullptr;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, k, v, v, (int)(cap > 0 ? cap : 1), 0, 64);
-    if (e != cudaSuccess) { cudaGetLastError(); bytes = (size_t)(cap > 0 ? cap : 1) * 16 + (1u << 20); }   // conservative fallback
-    return bytes;
-}
-
-size_t geom_total(int P) { GeomLayout L(P); return L.total + align_up((size_t)(P > 0 ? P : 1) * kGradRecFloats * 4, 256); }
+constexpr size_t kMaxTileSmem = 200 * 1024;      // tile-histogram rows live in shared memory: up to 51200 tiles
 
 template <int DEG, bool HAS_SH, bool HAS_COV>
 void launch_pre_fwd(const DgrSettings *s, const DgrGaussians *g, int *radii, char *geom, const GeomLayout &L, cudaStream_t st) {
-    preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV><<<L.nblocks, kPreThreads, 0, st>>>(
+    const size_t smem = (size_t)L.tiles * 4;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV><<<L.nblocks, kPreThreads, smem, st>>>(
         g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
         s->campos, g->means3D, g->shs, g->colors_precomp, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii,
-        reinterpret_cast<GeomHeader *>(geom), reinterpret_cast<unsigned long long *>(geom + L.off_status),
-        reinterpret_cast<Rec *>(geom + L.off_rec), reinterpret_cast<unsigned *>(geom + L.off_offsets),
-        reinterpret_cast<unsigned *>(geom + L.off_touched), L.nblocks);
+        reinterpret_cast<Rec *>(geom + L.off_rec), reinterpret_cast<unsigned *>(geom + L.off_touched),
+        reinterpret_cast<unsigned *>(geom + L.off_blkhist), L.tiles, L.iters);
 }
 
 template <int DEG, bool HAS_SH, bool HAS_COV>
@@ -122,6 +111,18 @@ void launch_pre_bwd(const DgrSettings *s, const DgrGaussians *g, const int *radi
         o->dL_dmeans3D, o->dL_dmeans2D, o->dL_dshs, o->dL_dcolors_precomp, o->dL_dopacities, o->dL_dscales, o->dL_drotations,
         o->dL_dcov3D_precomp, o->accumulate);
 }
+
+#define DGR_DISPATCH(FN, ...)                                                                              \
+    do {                                                                                                   \
+        const bool sh_ = g->shs != nullptr, cov_ = g->cov3D_precomp != nullptr;                            \
+        if (!sh_) { if (cov_) FN<0, false, true>(__VA_ARGS__); else FN<0, false, false>(__VA_ARGS__); }     \
+        else switch (s->sh_degree) {                                                                       \
+            case 0: if (cov_) FN<0, true, true>(__VA_ARGS__); else FN<0, true, false>(__VA_ARGS__); break;  \
+            case 1: if (cov_) FN<1, true, true>(__VA_ARGS__); else FN<1, true, false>(__VA_ARGS__); break;  \
+            case 2: if (cov_) FN<2, true, true>(__VA_ARGS__); else FN<2, true, false>(__VA_ARGS__); break;  \
+            default: if (cov_) FN<3, true, true>(__VA_ARGS__); else FN<3, true, false>(__VA_ARGS__); break; \
+        }                                                                                                  \
+    } while (0)
 
 __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched, float *mean_px, float *depth, float *conic,
                                   float *rgb, int *aabb, unsigned *tiles_touched) {
@@ -138,18 +139,27 @@ __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched
     }
     if (tiles_touched) tiles_touched[g] = touched[g];
 }
+
+bool g_sort_attr_set = false;
+int g_big_grid = 148;
+// tuning knobs (dgr_set_tuning): pixels per lane of the render kernels, heaviest-first tile order on/off
+int g_ppl_fwd = 1, g_ppl_bwd = 1;
+bool g_no_order = false;
+bool g_emit_attr_set = false;
 }  // namespace
 
 extern "C" {
 
 int dgr_abi_version(void) { return DGR_ABI_VERSION; }
+const char *dgr_last_error(void) { return g_err.c_str(); }
+uint64_t dgr_launch_count(void) { return g_launches; }
+void dgr_reset_launch_count(void) { g_launches = 0; }
 
 void dgr_profile_enable(int on) {
     for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     g_prof.clear();
     g_prof_on = on != 0;
 }
-// Synchronises the recorded events; writes up to `max` (name, milliseconds) pairs, names as a '\n'-joined string.
 int dgr_profile_collect(char *names, size_t names_bytes, float *ms, int max) {
     int n = 0; size_t off = 0;
     if (names && names_bytes) names[0] = 0;
@@ -166,113 +176,111 @@ int dgr_profile_collect(char *names, size_t names_bytes, float *ms, int max) {
     g_prof.clear();
     return n;
 }
-const char *dgr_last_error(void) { return g_err.c_str(); }
-uint64_t dgr_launch_count(void) { return g_launches; }
-void dgr_reset_launch_count(void) { g_launches = 0; }
 
-size_t dgr_geom_bytes(int32_t P) { return geom_total(P); }
-size_t dgr_image_bytes(int32_t H, int32_t W) { ImageLayout L(H, W); return L.total + align_up((size_t)H * W * 4, 256); }
-size_t dgr_binning_bytes(uint64_t cap, int32_t H, int32_t W) {
-    (void)H; (void)W;
-    BinningLayout L(cap, sort_temp_bytes(cap));
-    return L.total;
+int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order) {
+    if ((ppl_fwd != 1 && ppl_fwd != 2 && ppl_fwd != 4) || (ppl_bwd != 1 && ppl_bwd != 2 && ppl_bwd != 4)) return fail(-1, "ppl must be 1, 2 or 4");
+    g_ppl_fwd = ppl_fwd; g_ppl_bwd = ppl_bwd; g_no_order = tile_order == 0;
+    return 0;
 }
 
-int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *geom_v, int32_t *radii,
-                           uint64_t *n_instances_host, void *stream) {
+void *dgr_event_create(void) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { fail(-1, "cudaEventCreate failed"); return nullptr; }
+    return (void *)e;
+}
+int dgr_event_synchronize(void *ev) { DGR_CUDA(cudaEventSynchronize((cudaEvent_t)ev)); return 0; }
+void dgr_event_destroy(void *ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
+
+size_t dgr_geom_bytes(int32_t P, int32_t H, int32_t W) { return GeomLayout(P, H, W).total; }
+size_t dgr_image_bytes(int32_t H, int32_t W) { return ImageLayout(H, W).total; }
+size_t dgr_binning_bytes(uint64_t cap, int32_t H, int32_t W) { (void)H; (void)W; return BinningLayout(cap).total; }
+
+int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *geom_v, void *image_v, int32_t *radii, void *stream) {
     if (int e = check_settings(s)) return e;
     if (int e = check_gaussians(s, g)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     char *geom = (char *)geom_v;
-    if (!geom) return fail(-1, "geom scratch is NULL");
-    GeomLayout L(g->P);
-    DGR_CUDA(cudaMemsetAsync(geom, 0, L.off_rec, st));
+    if (!geom || !image_v) return fail(-1, "geom / image scratch is NULL");
+    GeomLayout L(g->P, s->image_height, s->image_width);
+    if ((size_t)L.tiles * 4 > kMaxTileSmem) return fail(-3, "image has more than 51200 tiles (16x16): not supported");
     if (g->P > 0) {
         if (!radii) return fail(-1, "radii is NULL");
-        const bool sh = g->shs != nullptr, cov = g->cov3D_precomp != nullptr;
-        prof_begin("preprocess_fwd", st);
-        if (sh) {
-#define DGR_DISPATCH_DEG(D)                                                     \
-    case D:                                                                     \
-        if (cov) launch_pre_fwd<D, true, true>(s, g, radii, geom, L, st);       \
-        else launch_pre_fwd<D, true, false>(s, g, radii, geom, L, st);          \
-        break;
-            switch (s->sh_degree) { DGR_DISPATCH_DEG(0) DGR_DISPATCH_DEG(1) DGR_DISPATCH_DEG(2) DGR_DISPATCH_DEG(3) }
-#undef DGR_DISPATCH_DEG
-        } else {
-            if (cov) launch_pre_fwd<0, false, true>(s, g, radii, geom, L, st);
-            else launch_pre_fwd<0, false, false>(s, g, radii, geom, L, st);
-        }
-        prof_end(st);
-        DGR_LAUNCHED(st, s->debug);
+        DGR_KERNEL("preprocess_fwd", st, s->debug, DGR_DISPATCH(launch_pre_fwd, s, g, radii, geom, L, st));
+    } else {
+        DGR_CUDA(cudaMemsetAsync(geom + L.off_blkhist, 0, (size_t)L.nblocks * L.tiles * 4, st));
     }
-    if (n_instances_host)
-        DGR_CUDA(cudaMemcpyAsync(n_instances_host, geom, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     return 0;
 }
 
-int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v, void *binning_v,
-                       uint64_t capacity, void *image_v, const DgrImages *out, void *stream) {
+int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v, void *binning_v, uint64_t capacity,
+                       void *image_v, const DgrImages *out, uint64_t *n_instances_host, void *count_ready_event, void *stream) {
     if (int e = check_settings(s)) return e;
     if (!g || !geom_v || !image_v || !out) return fail(-1, "NULL argument");
     if (!out->color || !out->depth || !out->alpha) return fail(-1, "output images must not be NULL");
+    if (capacity > 0 && !binning_v) return fail(-1, "binning scratch is NULL");
+    if (capacity >= 0xffffffffull) return fail(-3, "capacity above 2^32-1 tile instances not supported");
     cudaStream_t st = (cudaStream_t)stream;
     char *geom = (char *)geom_v, *binning = (char *)binning_v, *image = (char *)image_v;
     const int H = s->image_height, W = s->image_width;
-    GeomLayout GL(g->P);
+    GeomLayout GL(g->P, H, W);
     ImageLayout IL(H, W);
-    const size_t tiles = (size_t)IL.gx * IL.gy;
+    BinningLayout BL(capacity);
+    const int tiles = IL.gx * IL.gy;
+    if ((size_t)tiles * 4 > kMaxTileSmem) return fail(-3, "image has more than 51200 tiles (16x16): not supported");
     uint2 *ranges = reinterpret_cast<uint2 *>(image + IL.off_ranges);
+    unsigned *tile_count = reinterpret_cast<unsigned *>(image + IL.off_count);
+    unsigned *blk_hist = reinterpret_cast<unsigned *>(geom + GL.off_blkhist);
     unsigned *n_contrib = reinterpret_cast<unsigned *>(image + IL.off_ncontrib);
-    DGR_CUDA(cudaMemsetAsync(ranges, 0, tiles * sizeof(uint2), st));
+    float *final_T = reinterpret_cast<float *>(image + IL.off_finalT);
+    GeomHeader *hdr = reinterpret_cast<GeomHeader *>(geom);
+    const Rec *rec = reinterpret_cast<const Rec *>(geom + GL.off_rec);
+    unsigned long long *keys = binning ? reinterpret_cast<unsigned long long *>(binning + BL.off_keys) : nullptr;
+    unsigned *ids = binning ? reinterpret_cast<unsigned *>(binning + BL.off_ids) : nullptr;
+    Rec *recs = binning ? reinterpret_cast<Rec *>(binning + BL.off_rec) : nullptr;
 
-    // v1: the instance count is read back (one host sync per forward, as the reference op does).
-    unsigned long long n_inst = 0;
-    DGR_CUDA(cudaMemcpyAsync(&n_inst, geom, sizeof(n_inst), cudaMemcpyDeviceToHost, st));
-    DGR_CUDA(cudaStreamSynchronize(st));
-    if (n_inst >= 0xffffffffull) return fail(-3, "more than 2^32-1 tile instances");
-    unsigned long long n = n_inst < capacity ? n_inst : capacity;
-    const Rec *rec_sorted = nullptr;
-    if (n > 0) {
-        if (!binning) return fail(-1, "binning scratch is NULL");
-        const size_t temp_bytes = sort_temp_bytes(capacity);
-        BinningLayout BL(capacity, temp_bytes);
-        unsigned long long *keys = reinterpret_cast<unsigned long long *>(binning + BL.off_keys);
-        unsigned long long *keys_alt = reinterpret_cast<unsigned long long *>(binning + BL.off_keys_alt);
-        unsigned *vals = reinterpret_cast<unsigned *>(binning + BL.off_vals);
-        unsigned *vals_alt = reinterpret_cast<unsigned *>(binning + BL.off_vals_alt);
-        Rec *recs = reinterpret_cast<Rec *>(binning + BL.off_rec);
-        const Rec *rec = reinterpret_cast<const Rec *>(geom + GL.off_rec);
-        prof_begin("emit_instances", st);
-        emit_instances_kernel<<<(g->P + 255) / 256, 256, 0, st>>>(
-            g->P, IL.gx, rec, reinterpret_cast<const unsigned *>(geom + GL.off_offsets),
-            reinterpret_cast<const unsigned *>(geom + GL.off_touched), capacity, keys, vals);
-        prof_end(st);
-        DGR_LAUNCHED(st, s->debug);
-        int tile_bits = 0;
-        while (((size_t)1 << tile_bits) < tiles) tile_bits++;
-        size_t tb = temp_bytes;
-        prof_begin("radix_sort(cub)", st);
-        DGR_CUDA(cub::DeviceRadixSort::SortPairs(binning + BL.off_temp, tb, keys, keys_alt, vals, vals_alt, (int)n, 0, 32 + tile_bits, st));
-        prof_end(st);
-        g_launches += 1;   // counted as one library step (CUB launches several kernels internally)
-        prof_begin("ranges_gather", st);
-        ranges_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, keys_alt, vals_alt, rec, ranges, recs);
-        prof_end(st);
-        DGR_LAUNCHED(st, s->debug);
-        rec_sorted = recs;
+    DGR_KERNEL("tile_colscan", st, s->debug,
+               tile_colscan_kernel<<<(tiles + 31) / 32, 1024, 0, st>>>(tiles, GL.nblocks, blk_hist, tile_count));
+    unsigned *tile_order = reinterpret_cast<unsigned *>(image + IL.off_order);
+    unsigned *big_list = reinterpret_cast<unsigned *>(image + IL.off_biglist);
+    TileWork *work = reinterpret_cast<TileWork *>(image + IL.off_work);
+    DGR_KERNEL("tile_scan", st, s->debug,
+               tile_scan_kernel<<<1, 1024, 0, st>>>(tiles, tile_count, (unsigned long long)capacity, ranges, hdr, tile_order, work, big_list));
+    if (n_instances_host)
+        DGR_CUDA(cudaMemcpyAsync(n_instances_host, geom, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    if (count_ready_event) DGR_CUDA(cudaEventRecord((cudaEvent_t)count_ready_event, st));
+    if (g->P > 0 && capacity > 0) {
+        const size_t smem = (size_t)tiles * 4;
+        if (smem > 48 * 1024 && !g_emit_attr_set) {
+            DGR_CUDA(cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileSmem));
+            g_emit_attr_set = true;
+        }
+        DGR_KERNEL("emit_instances", st, s->debug,
+                   emit_instances_kernel<<<GL.nblocks, kPreThreads, smem, st>>>(
+                       g->P, IL.gx, tiles, GL.iters, rec, reinterpret_cast<const unsigned *>(geom + GL.off_touched), ranges, blk_hist, keys));
+        using SmS = SortSmem<kSortSmallThreads, kSortSmallCap>;
+        using SmB = SortSmem<kSortBigThreads, kSortBigCap>;
+        if (!g_sort_attr_set) {
+            DGR_CUDA(cudaFuncSetAttribute(tile_sort_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmS::bytes));
+            DGR_CUDA(cudaFuncSetAttribute(tile_sort_gather_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmB::bytes));
+            g_sort_attr_set = true;
+        }
+        DGR_KERNEL("tile_sort_gather", st, s->debug,
+                   tile_sort_gather_kernel<<<tiles, kSortSmallThreads, SmS::bytes, st>>>(tile_order, ranges, keys, rec, ids, recs));
+        DGR_KERNEL("tile_sort_gather_big", st, s->debug,
+                   tile_sort_gather_big_kernel<<<g_big_grid, kSortBigThreads, SmB::bytes, st>>>(work, big_list, ranges, keys, rec, ids, recs));
     }
-    float *final_T = reinterpret_cast<float *>(image + IL.total);
-    prof_begin("render_fwd", st);
-    render_fwd_kernel<<<(unsigned)tiles, kTileThreads, 0, st>>>(H, W, IL.gx, ranges, rec_sorted, s->bg, out->color, out->depth,
-                                                               out->alpha, n_contrib, final_T);
-    prof_end(st);
-    DGR_LAUNCHED(st, s->debug);
+    const unsigned *render_order = g_no_order ? nullptr : tile_order;
+#define DGR_RENDER_FWD(PPL_)                                                                                   \
+    DGR_KERNEL("render_fwd", st, s->debug,                                                                      \
+               render_fwd_kernel<PPL_><<<(unsigned)tiles, kTileThreads / PPL_, 0, st>>>(                        \
+                   H, W, IL.gx, render_order, ranges, recs, s->bg, out->color, out->depth, out->alpha, n_contrib, final_T))
+    if (g_ppl_fwd == 4) DGR_RENDER_FWD(4); else if (g_ppl_fwd == 2) DGR_RENDER_FWD(2); else DGR_RENDER_FWD(1);
+#undef DGR_RENDER_FWD
     return 0;
 }
 
-int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, const void *binning_v,
-                 uint64_t capacity, const void *image_v, const int32_t *radii, const float *out_alpha, const DgrImageGrads *gin,
+int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, const void *binning_v, uint64_t capacity,
+                 const void *image_v, const int32_t *radii, const float *out_alpha, const DgrImageGrads *gin,
                  const DgrGaussianGrads *gout, void *stream) {
     (void)out_alpha;
     if (int e = check_settings(s)) return e;
@@ -284,40 +292,25 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
     char *geom = (char *)geom_v;
     const char *binning = (const char *)binning_v, *image = (const char *)image_v;
     const int H = s->image_height, W = s->image_width;
-    GeomLayout GL(g->P);
+    GeomLayout GL(g->P, H, W);
     ImageLayout IL(H, W);
-    const size_t tiles = (size_t)IL.gx * IL.gy;
-    float *grad_rec = reinterpret_cast<float *>(geom + GL.total);
+    BinningLayout BL(capacity);
+    const int tiles = IL.gx * IL.gy;
+    float *grad_rec = reinterpret_cast<float *>(geom + GL.off_gradrec);
     DGR_CUDA(cudaMemsetAsync(grad_rec, 0, (size_t)g->P * kGradRecFloats * 4, st));
     if (binning && capacity > 0) {
-        const uint64_t cap = capacity;
-        BinningLayout BL(cap, sort_temp_bytes(cap));
-        const unsigned *ids_sorted = reinterpret_cast<const unsigned *>(binning + BL.off_vals_alt);
-        const Rec *recs = reinterpret_cast<const Rec *>(binning + BL.off_rec);
-        const float *final_T = reinterpret_cast<const float *>(image + IL.total);
-        prof_begin("render_bwd", st);
-        render_bwd_kernel<<<(unsigned)tiles, kTileThreads, 0, st>>>(
-            H, W, IL.gx, reinterpret_cast<const uint2 *>(image + IL.off_ranges), recs, ids_sorted, s->bg, final_T,
-            reinterpret_cast<const unsigned *>(image + IL.off_ncontrib), gin->dL_dcolor, gin->dL_ddepth, gin->dL_dalpha, grad_rec);
-        prof_end(st);
-        DGR_LAUNCHED(st, s->debug);
+        const unsigned *tile_order = g_no_order ? nullptr : reinterpret_cast<const unsigned *>(image + IL.off_order);
+#define DGR_RENDER_BWD(PPL_)                                                                                              \
+    DGR_KERNEL("render_bwd", st, s->debug,                                                                                 \
+               render_bwd_kernel<PPL_><<<(unsigned)tiles, kTileThreads / PPL_, 0, st>>>(                                   \
+                   H, W, IL.gx, tile_order, reinterpret_cast<const uint2 *>(image + IL.off_ranges),                        \
+                   reinterpret_cast<const Rec *>(binning + BL.off_rec), reinterpret_cast<const unsigned *>(binning + BL.off_ids), \
+                   s->bg, reinterpret_cast<const float *>(image + IL.off_finalT),                                          \
+                   reinterpret_cast<const unsigned *>(image + IL.off_ncontrib), gin->dL_dcolor, gin->dL_ddepth, gin->dL_dalpha, grad_rec))
+        if (g_ppl_bwd == 4) DGR_RENDER_BWD(4); else if (g_ppl_bwd == 2) DGR_RENDER_BWD(2); else DGR_RENDER_BWD(1);
+#undef DGR_RENDER_BWD
     }
-    const bool sh = g->shs != nullptr, cov = g->cov3D_precomp != nullptr;
-    prof_begin("preprocess_bwd", st);
-    if (sh) {
-#define DGR_DISPATCH_DEG(D)                                                       \
-    case D:                                                                       \
-        if (cov) launch_pre_bwd<D, true, true>(s, g, radii, grad_rec, gout, st);  \
-        else launch_pre_bwd<D, true, false>(s, g, radii, grad_rec, gout, st);     \
-        break;
-        switch (s->sh_degree) { DGR_DISPATCH_DEG(0) DGR_DISPATCH_DEG(1) DGR_DISPATCH_DEG(2) DGR_DISPATCH_DEG(3) }
-#undef DGR_DISPATCH_DEG
-    } else {
-        if (cov) launch_pre_bwd<0, false, true>(s, g, radii, grad_rec, gout, st);
-        else launch_pre_bwd<0, false, false>(s, g, radii, grad_rec, gout, st);
-    }
-    prof_end(st);
-    DGR_LAUNCHED(st, s->debug);
+    DGR_KERNEL("preprocess_bwd", st, s->debug, DGR_DISPATCH(launch_pre_bwd, s, g, radii, grad_rec, gout, st));
     return 0;
 }
 
@@ -327,22 +320,21 @@ int dgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, c
     if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(-1, "bad argument");
     if (P == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    mark_visible_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, viewmatrix, present);
-    DGR_LAUNCHED(st, 0);
+    DGR_KERNEL("mark_visible", st, 0, mark_visible_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, viewmatrix, present));
     return 0;
 }
 
-int dgr_debug_geom(int32_t P, const void *geom_v, float *mean_px, float *depth, float *conic, float *rgb,
+int dgr_debug_geom(int32_t P, int32_t H, int32_t W, const void *geom_v, float *mean_px, float *depth, float *conic, float *rgb,
                    int32_t *aabb, uint32_t *tiles_touched, void *stream) {
     if (P <= 0) return 0;
     if (!geom_v) return fail(-1, "geom is NULL");
     const char *geom = (const char *)geom_v;
-    GeomLayout L(P);
+    GeomLayout L(P, H, W);
     cudaStream_t st = (cudaStream_t)stream;
-    debug_geom_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, reinterpret_cast<const Rec *>(geom + L.off_rec),
-                                                     reinterpret_cast<const unsigned *>(geom + L.off_touched), mean_px, depth,
-                                                     conic, rgb, aabb, tiles_touched);
-    DGR_LAUNCHED(st, 0);
+    DGR_KERNEL("debug_geom", st, 0,
+               debug_geom_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, reinterpret_cast<const Rec *>(geom + L.off_rec),
+                                                                reinterpret_cast<const unsigned *>(geom + L.off_touched), mean_px,
+                                                                depth, conic, rgb, aabb, tiles_touched));
     return 0;
 }
 

@@ -37,6 +37,45 @@ __device__ __forceinline__ void sh_basis_grad(float x, float y, float z, float (
 
 __device__ __forceinline__ void store_acc(float *p, float v, bool acc) { *p = acc ? (*p + v) : v; }
 
+// Coalesced write of the SH gradient rows of one warp's 32 Gaussians.  Each lane owns one row (3M floats, of which
+// the first 3*NB are bs[k]*gr[ch] and the rest zero); writing them directly would make every store instruction touch
+// 32 different cache lines.  Instead the rows are transposed through shared memory in chunks of 24 floats
+// (row stride 25 words: conflict-free) and written back with consecutive lanes on consecutive addresses.
+template <int DEG>
+__device__ __forceinline__ void store_sh_grads(float *__restrict__ dL_dshs, int P, int M, const float (&bs)[16],
+                                               const float (&gr)[3], bool acc, float *stage /* [32*25] of this warp */) {
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    const int lane = threadIdx.x & 31;
+    const int row_base = (int)(blockIdx.x * blockDim.x) + (int)(threadIdx.x & ~31u);
+    const int nrows = min(32, P - row_base);
+    if (nrows <= 0) return;
+    const int rowlen = 3 * M;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        if (24 * c < rowlen) {
+#pragma unroll
+            for (int j = 0; j < 24; j++) {
+                const int f = 24 * c + j;                 // compile-time
+                const float v = (f / 3 < NB) ? bs[(f / 3) < 16 ? (f / 3) : 0] * gr[f % 3] : 0.f;
+                if (f < rowlen) stage[lane * 25 + j] = v;
+            }
+            __syncwarp();
+            const int cw = min(24, rowlen - 24 * c);
+            const unsigned inv = (65536u + (unsigned)cw - 1u) / (unsigned)cw;      // exact idx / cw for idx < 32 * 24
+            for (int it = 0; it < cw; it++) {
+                const int idx = it * 32 + lane;
+                const int row = (int)(((unsigned)idx * inv) >> 16), col = idx - row * cw;
+                if (row < nrows) {
+                    float *dst = dL_dshs + (size_t)(row_base + row) * rowlen + 24 * c + col;
+                    const float v = stage[row * 25 + col];
+                    *dst = acc ? (*dst + v) : v;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 template <int DEG, bool HAS_SH, bool HAS_COV>
 __global__ void __launch_bounds__(kPreThreads)
 preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, float scale_modifier,
@@ -50,189 +89,186 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                       float *__restrict__ dL_dcolors, float *__restrict__ dL_dopacities, float *__restrict__ dL_dscales,
                       float *__restrict__ dL_drotations, float *__restrict__ dL_dcov3D, int accumulate) {
     __shared__ FrameConsts fc;
+    __shared__ float s_stage[HAS_SH ? (kPreThreads / 32) * 32 * 25 : 1];
     load_frame(fc, viewmatrix, projmatrix, HAS_SH ? campos : nullptr);
     __syncthreads();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= P) return;
     const bool acc = accumulate != 0;
     constexpr int NB = (DEG + 1) * (DEG + 1);
-    const bool visible = radii[g] > 0;
-    if (!visible) {
-        if (acc) return;
+    const bool in_range = g < P;
+    const bool visible = in_range && radii[g] > 0;
+    float bs[16];
+    float gr[3] = { 0.f, 0.f, 0.f };
+#pragma unroll
+    for (int k = 0; k < 16; k++) bs[k] = 0.f;
+
+    if (in_range && !visible && !acc) {
         if (dL_dmeans3D) { dL_dmeans3D[3 * (size_t)g] = 0.f; dL_dmeans3D[3 * (size_t)g + 1] = 0.f; dL_dmeans3D[3 * (size_t)g + 2] = 0.f; }
         if (dL_dmeans2D) { dL_dmeans2D[3 * (size_t)g] = 0.f; dL_dmeans2D[3 * (size_t)g + 1] = 0.f; dL_dmeans2D[3 * (size_t)g + 2] = 0.f; }
-        if (HAS_SH && dL_dshs) for (int k = 0; k < 3 * M; k++) dL_dshs[(size_t)g * M * 3 + k] = 0.f;
         if (!HAS_SH && dL_dcolors) { dL_dcolors[3 * (size_t)g] = 0.f; dL_dcolors[3 * (size_t)g + 1] = 0.f; dL_dcolors[3 * (size_t)g + 2] = 0.f; }
         if (dL_dopacities) dL_dopacities[g] = 0.f;
         if (!HAS_COV && dL_dscales) { dL_dscales[3 * (size_t)g] = 0.f; dL_dscales[3 * (size_t)g + 1] = 0.f; dL_dscales[3 * (size_t)g + 2] = 0.f; }
         if (!HAS_COV && dL_drotations) { for (int k = 0; k < 4; k++) dL_drotations[4 * (size_t)g + k] = 0.f; }
         if (HAS_COV && dL_dcov3D) { for (int k = 0; k < 6; k++) dL_dcov3D[6 * (size_t)g + k] = 0.f; }
-        return;
     }
-    const float4 m0 = ldg_f4(grad_rec + (size_t)g * kGradRecFloats);
-    const float4 m1 = ldg_f4(grad_rec + (size_t)g * kGradRecFloats + 4);
-    const float4 m2 = ldg_f4(grad_rec + (size_t)g * kGradRecFloats + 8);
-    // moments: m0 = {u, u dx, u dy, u dx^2}, m1 = {u dx dy, u dy^2, wr, wg}, m2 = {wb, wd, -, -}
-    const float3 p = make_float3(__ldg(means3D + 3 * (size_t)g), __ldg(means3D + 3 * (size_t)g + 1), __ldg(means3D + 3 * (size_t)g + 2));
-    float S6[6];
-    float R[9];
-    float3 s = make_float3(0.f, 0.f, 0.f);
-    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
-    if (HAS_COV) {
+    if (visible) {
+        const float4 m0 = ldg_f4(grad_rec + (size_t)g * kGradRecFloats);
+        const float4 m1 = ldg_f4(grad_rec + (size_t)g * kGradRecFloats + 4);
+        const float4 m2 = ldg_f4(grad_rec + (size_t)g * kGradRecFloats + 8);
+        // moments: m0 = {u, u dx, u dy, u dx^2}, m1 = {u dx dy, u dy^2, wr, wg}, m2 = {wb, wd, -, -}
+        const float3 p = make_float3(__ldg(means3D + 3 * (size_t)g), __ldg(means3D + 3 * (size_t)g + 1), __ldg(means3D + 3 * (size_t)g + 2));
+        float S6[6];
+        float R[9];
+        float3 s = make_float3(0.f, 0.f, 0.f);
+        float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (HAS_COV) {
 #pragma unroll
-        for (int i = 0; i < 6; i++) S6[i] = __ldg(cov3D_precomp + 6 * (size_t)g + i);
-    } else {
-        s = make_float3(scale_modifier * __ldg(scales + 3 * (size_t)g), scale_modifier * __ldg(scales + 3 * (size_t)g + 1),
-                        scale_modifier * __ldg(scales + 3 * (size_t)g + 2));
-        q = ldg_f4(rotations + 4 * (size_t)g);
-        quat_to_R(q, R);
-        cov3d_from_scale_rot(s, R, S6);
-    }
-    const float fx = (float)W / (2.f * tanfovx), fy = (float)H / (2.f * tanfovy);
-    Geo geo;
-    project_geo(fc, p, S6, fx, fy, DGR_FOV_CLAMP * tanfovx, DGR_FOV_CLAMP * tanfovy, geo);
-    const float a = geo.cxx, b = geo.cxy, c = geo.cyy;
-    const float det = a * c - b * b, di = 1.f / det;
-    const float cA = c * di, cB = -b * di, cC = a * di;
-    const float o = __ldg(opacities + g);
-
-    // pixel-space mean gradient and conic gradient from the moments
-    const float gpx = -(cA * m0.y + cB * m0.z), gpy = -(cC * m0.z + cB * m0.y);
-    const float gA = -0.5f * m0.w, gB = -m1.x, gC = -0.5f * m1.y;
-    const float g_op = (o != 0.f) ? m0.x / o : 0.f;
-    const float g_rgb[3] = { m1.z, m1.w, m2.x };
-    const float g_depth = m2.y;
-
-    float dmean[3] = { 0.f, 0.f, 0.f };
-    // (1) mean_px through the full projection; reported means2D grad is in NDC units
-    const float gndx = gpx * 0.5f * (float)W, gndy = gpy * 0.5f * (float)H;
-    if (dL_dmeans2D) {
-        store_acc(dL_dmeans2D + 3 * (size_t)g, gndx, acc); store_acc(dL_dmeans2D + 3 * (size_t)g + 1, gndy, acc);
-        if (!acc) dL_dmeans2D[3 * (size_t)g + 2] = 0.f;
-    }
-    {
-        const float *PM = fc.PM;
-        const float mul1 = geo.ndcx * geo.pw, mul2 = geo.ndcy * geo.pw;     // ph.x * pw^2, ph.y * pw^2
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-            dmean[k] += (PM[4 * k] * geo.pw - PM[4 * k + 3] * mul1) * gndx + (PM[4 * k + 1] * geo.pw - PM[4 * k + 3] * mul2) * gndy;
-    }
-    // (4) depth = t.z
-#pragma unroll
-    for (int k = 0; k < 3; k++) dmean[k] += fc.V[4 * k + 2] * g_depth;
-    // (3) colour
-    if (HAS_SH) {
-        float dx = p.x - fc.cam[0], dy = p.y - fc.cam[1], dz = p.z - fc.cam[2];
-        const float il = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
-        dx *= il; dy *= il; dz *= il;
-        float bs[16]; sh_basis<DEG>(dx, dy, dz, bs);
-        float cf[48];
-        load_sh_row<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, cf);
-        float rgb[3] = { 0.f, 0.f, 0.f };
-#pragma unroll
-        for (int k = 0; k < NB; k++) { rgb[0] += bs[k] * cf[3 * k]; rgb[1] += bs[k] * cf[3 * k + 1]; rgb[2] += bs[k] * cf[3 * k + 2]; }
-        float gr[3];
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) gr[ch] = (rgb[ch] + DGR_SH_OFFSET < 0.f) ? 0.f : g_rgb[ch];
-        float dbx[16], dby[16], dbz[16];
-        sh_basis_grad<DEG>(dx, dy, dz, dbx, dby, dbz);
-        float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-#pragma unroll
-        for (int k = 0; k < NB; k++) {
-            const float dotc = cf[3 * k] * gr[0] + cf[3 * k + 1] * gr[1] + cf[3 * k + 2] * gr[2];
-            ddx += dbx[k] * dotc; ddy += dby[k] * dotc; ddz += dbz[k] * dotc;
+            for (int i = 0; i < 6; i++) S6[i] = __ldg(cov3D_precomp + 6 * (size_t)g + i);
+        } else {
+            s = make_float3(scale_modifier * __ldg(scales + 3 * (size_t)g), scale_modifier * __ldg(scales + 3 * (size_t)g + 1),
+                            scale_modifier * __ldg(scales + 3 * (size_t)g + 2));
+            q = ldg_f4(rotations + 4 * (size_t)g);
+            quat_to_R(q, R);
+            cov3d_from_scale_rot(s, R, S6);
         }
-        if (dL_dshs) {
-            float *out = dL_dshs + (size_t)g * M * 3;
-#pragma unroll
-            for (int k = 0; k < NB; k++) {
-                store_acc(out + 3 * k, bs[k] * gr[0], acc); store_acc(out + 3 * k + 1, bs[k] * gr[1], acc); store_acc(out + 3 * k + 2, bs[k] * gr[2], acc);
-            }
-            if (!acc) for (int k = 3 * NB; k < 3 * M; k++) out[k] = 0.f;
-        }
-        const float dot = dx * ddx + dy * ddy + dz * ddz;
-        dmean[0] += (ddx - dx * dot) * il; dmean[1] += (ddy - dy * dot) * il; dmean[2] += (ddz - dz * dot) * il;
-    } else if (dL_dcolors) {
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) store_acc(dL_dcolors + 3 * (size_t)g + ch, g_rgb[ch], acc);
-    }
-    if (dL_dopacities) store_acc(dL_dopacities + g, g_op, acc);
+        const float fx = (float)W / (2.f * tanfovx), fy = (float)H / (2.f * tanfovy);
+        Geo geo;
+        project_geo(fc, p, S6, fx, fy, DGR_FOV_CLAMP * tanfovx, DGR_FOV_CLAMP * tanfovy, geo);
+        const float a = geo.cxx, b = geo.cxy, c = geo.cyy;
+        const float det = a * c - b * b, di = 1.f / det;
+        const float cA = c * di, cB = -b * di, cC = a * di;
+        const float o = __ldg(opacities + g);
 
-    // (2) conic -> cov2D -> (Sigma, T = J Rwv)
-    const float d2 = di * di;
-    const float ga = d2 * (-c * c * gA + b * c * gB - b * b * gC);
-    const float gc = d2 * (-b * b * gA + a * b * gB - a * a * gC);
-    const float gb = d2 * (2.f * b * c * gA - (det + 2.f * b * b) * gB + 2.f * a * b * gC);
-    const float G00 = ga, G01 = 0.5f * gb, G11 = gc;
-    const float *T0 = geo.T0, *T1 = geo.T1;
-    float dS[9];
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-#pragma unroll
-        for (int l = 0; l < 3; l++)
-            dS[3 * k + l] = T0[k] * (G00 * T0[l] + G01 * T1[l]) + T1[k] * (G01 * T0[l] + G11 * T1[l]);
-    const float Sg[9] = { S6[0], S6[1], S6[2], S6[1], S6[3], S6[4], S6[2], S6[4], S6[5] };
-    float TS0[3], TS1[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        TS0[k] = T0[0] * Sg[k] + T0[1] * Sg[3 + k] + T0[2] * Sg[6 + k];
-        TS1[k] = T1[0] * Sg[k] + T1[1] * Sg[3 + k] + T1[2] * Sg[6 + k];
-    }
-    float dT0[3], dT1[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) { dT0[k] = 2.f * (G00 * TS0[k] + G01 * TS1[k]); dT1[k] = 2.f * (G01 * TS0[k] + G11 * TS1[k]); }
-    float dJ00 = 0.f, dJ02 = 0.f, dJ11 = 0.f, dJ12 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        dJ00 += dT0[k] * fc.V[4 * k]; dJ02 += dT0[k] * fc.V[4 * k + 2];
-        dJ11 += dT1[k] * fc.V[4 * k + 1]; dJ12 += dT1[k] * fc.V[4 * k + 2];
-    }
-    const float tz = geo.t[2];
-    const float tz2 = 1.f / (tz * tz), tz3 = tz2 / tz;
-    const float dtx = geo.clx ? 0.f : -fx * tz2 * dJ02;
-    const float dty = geo.cly ? 0.f : -fy * tz2 * dJ12;
-    const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + 2.f * fx * geo.tx * tz3 * dJ02 + 2.f * fy * geo.ty * tz3 * dJ12;
-#pragma unroll
-    for (int k = 0; k < 3; k++) dmean[k] += fc.V[4 * k] * dtx + fc.V[4 * k + 1] * dty + fc.V[4 * k + 2] * dtz;
-    if (dL_dmeans3D) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) store_acc(dL_dmeans3D + 3 * (size_t)g + k, dmean[k], acc);
-    }
-    if (HAS_COV) {
-        if (dL_dcov3D) {
-            float *out = dL_dcov3D + 6 * (size_t)g;
-            store_acc(out, dS[0], acc); store_acc(out + 1, 2.f * dS[1], acc); store_acc(out + 2, 2.f * dS[2], acc);
-            store_acc(out + 3, dS[4], acc); store_acc(out + 4, 2.f * dS[5], acc); store_acc(out + 5, dS[8], acc);
+        // pixel-space mean gradient and conic gradient from the moments
+        const float gpx = -(cA * m0.y + cB * m0.z), gpy = -(cC * m0.z + cB * m0.y);
+        const float gA = -0.5f * m0.w, gB = -m1.x, gC = -0.5f * m1.y;
+        const float g_op = (o != 0.f) ? m0.x / o : 0.f;
+        const float g_rgb[3] = { m1.z, m1.w, m2.x };
+        const float g_depth = m2.y;
+
+        float dmean[3] = { 0.f, 0.f, 0.f };
+        // (1) mean_px through the full projection; reported means2D grad is in NDC units
+        const float gndx = gpx * 0.5f * (float)W, gndy = gpy * 0.5f * (float)H;
+        if (dL_dmeans2D) {
+            store_acc(dL_dmeans2D + 3 * (size_t)g, gndx, acc); store_acc(dL_dmeans2D + 3 * (size_t)g + 1, gndy, acc);
+            if (!acc) dL_dmeans2D[3 * (size_t)g + 2] = 0.f;
         }
-    } else {
-        // Sigma = Mx Mx^T, Mx = R diag(s):  dL/dMx = 2 dS Mx
-        float Mx[9];
-#pragma unroll
-        for (int i = 0; i < 3; i++) { Mx[3 * i] = R[3 * i] * s.x; Mx[3 * i + 1] = R[3 * i + 1] * s.y; Mx[3 * i + 2] = R[3 * i + 2] * s.z; }
-        float dM[9];
-#pragma unroll
-        for (int i = 0; i < 3; i++)
+        {
+            const float *PM = fc.PM;
+            const float mul1 = geo.ndcx * geo.pw, mul2 = geo.ndcy * geo.pw;     // ph.x * pw^2, ph.y * pw^2
 #pragma unroll
             for (int k = 0; k < 3; k++)
-                dM[3 * i + k] = 2.f * (dS[3 * i] * Mx[k] + dS[3 * i + 1] * Mx[3 + k] + dS[3 * i + 2] * Mx[6 + k]);
-        const float sv[3] = { s.x, s.y, s.z };
-        float dR[9];
+                dmean[k] += (PM[4 * k] * geo.pw - PM[4 * k + 3] * mul1) * gndx + (PM[4 * k + 1] * geo.pw - PM[4 * k + 3] * mul2) * gndy;
+        }
+        // (4) depth = t.z
+#pragma unroll
+        for (int k = 0; k < 3; k++) dmean[k] += fc.V[4 * k + 2] * g_depth;
+        // (3) colour
+        if (HAS_SH) {
+            float dx = p.x - fc.cam[0], dy = p.y - fc.cam[1], dz = p.z - fc.cam[2];
+            const float il = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
+            dx *= il; dy *= il; dz *= il;
+            sh_basis<DEG>(dx, dy, dz, bs);
+            float cf[48];
+            load_sh_row<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, cf);
+            float rgb[3] = { 0.f, 0.f, 0.f };
+#pragma unroll
+            for (int k = 0; k < NB; k++) { rgb[0] += bs[k] * cf[3 * k]; rgb[1] += bs[k] * cf[3 * k + 1]; rgb[2] += bs[k] * cf[3 * k + 2]; }
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) gr[ch] = (rgb[ch] + DGR_SH_OFFSET < 0.f) ? 0.f : g_rgb[ch];
+            float dbx[16], dby[16], dbz[16];
+            sh_basis_grad<DEG>(dx, dy, dz, dbx, dby, dbz);
+            float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+#pragma unroll
+            for (int k = 0; k < NB; k++) {
+                const float dotc = cf[3 * k] * gr[0] + cf[3 * k + 1] * gr[1] + cf[3 * k + 2] * gr[2];
+                ddx += dbx[k] * dotc; ddy += dby[k] * dotc; ddz += dbz[k] * dotc;
+            }
+            const float dot = dx * ddx + dy * ddy + dz * ddz;
+            dmean[0] += (ddx - dx * dot) * il; dmean[1] += (ddy - dy * dot) * il; dmean[2] += (ddz - dz * dot) * il;
+        } else if (dL_dcolors) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) store_acc(dL_dcolors + 3 * (size_t)g + ch, g_rgb[ch], acc);
+        }
+        if (dL_dopacities) store_acc(dL_dopacities + g, g_op, acc);
+
+        // (2) conic -> cov2D -> (Sigma, T = J Rwv)
+        const float d2 = di * di;
+        const float ga = d2 * (-c * c * gA + b * c * gB - b * b * gC);
+        const float gc = d2 * (-b * b * gA + a * b * gB - a * a * gC);
+        const float gb = d2 * (2.f * b * c * gA - (det + 2.f * b * b) * gB + 2.f * a * b * gC);
+        const float G00 = ga, G01 = 0.5f * gb, G11 = gc;
+        const float *T0 = geo.T0, *T1 = geo.T1;
+        float dS[9];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int l = 0; l < 3; l++)
+                dS[3 * k + l] = T0[k] * (G00 * T0[l] + G01 * T1[l]) + T1[k] * (G01 * T0[l] + G11 * T1[l]);
+        const float Sg[9] = { S6[0], S6[1], S6[2], S6[1], S6[3], S6[4], S6[2], S6[4], S6[5] };
+        float TS0[3], TS1[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            float v = 0.f;
-#pragma unroll
-            for (int i = 0; i < 3; i++) { v += dM[3 * i + k] * R[3 * i + k]; dR[3 * i + k] = dM[3 * i + k] * sv[k]; }
-            if (dL_dscales) store_acc(dL_dscales + 3 * (size_t)g + k, v * scale_modifier, acc);
+            TS0[k] = T0[0] * Sg[k] + T0[1] * Sg[3 + k] + T0[2] * Sg[6 + k];
+            TS1[k] = T1[0] * Sg[k] + T1[1] * Sg[3 + k] + T1[2] * Sg[6 + k];
         }
-        if (dL_drotations) {
-            const float r = q.x, x = q.y, y = q.z, z = q.w;
-            float *out = dL_drotations + 4 * (size_t)g;
-            store_acc(out, 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]), acc);
-            store_acc(out + 1, 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]), acc);
-            store_acc(out + 2, 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]), acc);
-            store_acc(out + 3, 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]), acc);
+        float dT0[3], dT1[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { dT0[k] = 2.f * (G00 * TS0[k] + G01 * TS1[k]); dT1[k] = 2.f * (G01 * TS0[k] + G11 * TS1[k]); }
+        float dJ00 = 0.f, dJ02 = 0.f, dJ11 = 0.f, dJ12 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            dJ00 += dT0[k] * fc.V[4 * k]; dJ02 += dT0[k] * fc.V[4 * k + 2];
+            dJ11 += dT1[k] * fc.V[4 * k + 1]; dJ12 += dT1[k] * fc.V[4 * k + 2];
+        }
+        const float tz = geo.t[2];
+        const float tz2 = 1.f / (tz * tz), tz3 = tz2 / tz;
+        const float dtx = geo.clx ? 0.f : -fx * tz2 * dJ02;
+        const float dty = geo.cly ? 0.f : -fy * tz2 * dJ12;
+        const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + 2.f * fx * geo.tx * tz3 * dJ02 + 2.f * fy * geo.ty * tz3 * dJ12;
+#pragma unroll
+        for (int k = 0; k < 3; k++) dmean[k] += fc.V[4 * k] * dtx + fc.V[4 * k + 1] * dty + fc.V[4 * k + 2] * dtz;
+        if (dL_dmeans3D) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) store_acc(dL_dmeans3D + 3 * (size_t)g + k, dmean[k], acc);
+        }
+        if (HAS_COV) {
+            if (dL_dcov3D) {
+                float *out = dL_dcov3D + 6 * (size_t)g;
+                store_acc(out, dS[0], acc); store_acc(out + 1, 2.f * dS[1], acc); store_acc(out + 2, 2.f * dS[2], acc);
+                store_acc(out + 3, dS[4], acc); store_acc(out + 4, 2.f * dS[5], acc); store_acc(out + 5, dS[8], acc);
+            }
+        } else {
+            // Sigma = Mx Mx^T, Mx = R diag(s):  dL/dMx = 2 dS Mx
+            float Mx[9];
+#pragma unroll
+            for (int i = 0; i < 3; i++) { Mx[3 * i] = R[3 * i] * s.x; Mx[3 * i + 1] = R[3 * i + 1] * s.y; Mx[3 * i + 2] = R[3 * i + 2] * s.z; }
+            float dM[9];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    dM[3 * i + k] = 2.f * (dS[3 * i] * Mx[k] + dS[3 * i + 1] * Mx[3 + k] + dS[3 * i + 2] * Mx[6 + k]);
+            const float sv[3] = { s.x, s.y, s.z };
+            float dR[9];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float v = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3; i++) { v += dM[3 * i + k] * R[3 * i + k]; dR[3 * i + k] = dM[3 * i + k] * sv[k]; }
+                if (dL_dscales) store_acc(dL_dscales + 3 * (size_t)g + k, v * scale_modifier, acc);
+            }
+            if (dL_drotations) {
+                const float r = q.x, x = q.y, y = q.z, z = q.w;
+                float *out = dL_drotations + 4 * (size_t)g;
+                store_acc(out, 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]), acc);
+                store_acc(out + 1, 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]), acc);
+                store_acc(out + 2, 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]), acc);
+                store_acc(out + 3, 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]), acc);
+            }
         }
     }
+    if (HAS_SH && dL_dshs) store_sh_grads<DEG>(dL_dshs, P, M, bs, gr, acc, s_stage + (threadIdx.x >> 5) * (32 * 25));
 }
 
 }  // namespace dgr

@@ -35,34 +35,47 @@ static_assert(sizeof(Rec) == 48, "Rec must be 48 bytes");
 constexpr int kGradRecFloats = 12;
 
 struct GeomHeader {
-    unsigned long long n_inst;     // total tile instances of this frame
-    unsigned int ticket;           // dynamic block id counter of the preprocess kernel
-    unsigned int pad[13];
+    unsigned long long n_inst;     // total tile instances of this frame (written by tile_scan_kernel)
+    unsigned int pad[14];
 };
 static_assert(sizeof(GeomHeader) == 64, "GeomHeader");
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// geom scratch: [header 256][status u64 x nblocks][rec 48 x P][offsets u32 x P][touched u32 x P]
+// Gaussians per block of the preprocess / emit kernels = kPreThreads * iters; iters grows so that the
+// [blocks x tiles] count matrix stays below 64 MB.
+__host__ __device__ inline int choose_gpb_iters(int P, int tiles) {
+    const size_t blocks1 = ((size_t)(P > 0 ? P : 1) + kPreThreads - 1) / kPreThreads;
+    const size_t bytes = blocks1 * (size_t)(tiles > 0 ? tiles : 1) * 4;
+    size_t k = (bytes + ((size_t)64 << 20) - 1) / ((size_t)64 << 20);
+    if (k < 1) k = 1;
+    if (k > 64) k = 64;
+    return (int)k;
+}
+
+// geom scratch: [header 256][rec 48 x P][touched u32 x P][moments 48 x P (backward)][count matrix u32 x blocks x tiles]
 struct GeomLayout {
-    size_t off_status, off_rec, off_offsets, off_touched, total;
-    int nblocks;
-    __host__ __device__ explicit GeomLayout(int P) {
-        nblocks = (P + kPreThreads - 1) / kPreThreads;
-        if (nblocks < 1) nblocks = 1;
+    size_t off_rec, off_touched, off_gradrec, off_blkhist, total;
+    int tiles, iters, nblocks;
+    __host__ __device__ GeomLayout(int P, int H, int W) {
         size_t Pn = P > 0 ? (size_t)P : 1;
+        tiles = ((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile);
+        if (tiles < 1) tiles = 1;
+        iters = choose_gpb_iters(P, tiles);
+        nblocks = (int)((Pn + (size_t)kPreThreads * iters - 1) / ((size_t)kPreThreads * iters));
         size_t o = 256;
-        off_status = o;  o = align_up(o + (size_t)nblocks * 8, 256);
         off_rec = o;     o = align_up(o + Pn * sizeof(Rec), 256);
-        off_offsets = o; o = align_up(o + Pn * 4, 256);
         off_touched = o; o = align_up(o + Pn * 4, 256);
+        off_gradrec = o; o = align_up(o + Pn * kGradRecFloats * 4, 256);
+        off_blkhist = o; o = align_up(o + (size_t)nblocks * tiles * 4, 256);
         total = o;
     }
 };
 
-// image scratch: [ranges uint2 x tiles][n_contrib u32 x H*W]
+// image scratch: [ranges uint2 x tiles][tile_count u32 x tiles][tile_order u32 x tiles][big_list u32 x tiles][work 256]
+//                [n_contrib u32 x HW][final_T f32 x HW]
 struct ImageLayout {
-    size_t off_ranges, off_ncontrib, total;
+    size_t off_ranges, off_count, off_order, off_biglist, off_work, off_ncontrib, off_finalT, total;
     int gx, gy;
     __host__ __device__ ImageLayout(int H, int W) {
         gx = (W + kTile - 1) / kTile; gy = (H + kTile - 1) / kTile;
@@ -70,7 +83,12 @@ struct ImageLayout {
         size_t hw = (size_t)H * W; if (hw < 1) hw = 1;
         size_t o = 0;
         off_ranges = o;   o = align_up(o + tiles * 8, 256);
+        off_count = o;    o = align_up(o + tiles * 4, 256);
+        off_order = o;    o = align_up(o + tiles * 4, 256);
+        off_biglist = o;  o = align_up(o + tiles * 4, 256);
+        off_work = o;     o = align_up(o + 256, 256);
         off_ncontrib = o; o = align_up(o + hw * 4, 256);
+        off_finalT = o;   o = align_up(o + hw * 4, 256);
         total = o;
     }
 };
@@ -109,8 +127,5 @@ __device__ __forceinline__ void red_add_f32(float *addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ float4 ldg_f4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
-
-// status word of the decoupled look-back scan: [63:62] flag, [61:0] value
-enum : unsigned long long { kFlagAggregate = 1ull << 62, kFlagPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1 };
 
 }  // namespace dgr

@@ -1,7 +1,7 @@
 // dgr_preprocess.cuh — per-Gaussian forward kernel (A2 of SURVEY.md §8a): frustum cull, cov3D, EWA cov2D, conic,
-// radius, pixel mean, SH -> RGB, opacity-aware pixel AABB, and — fused — the exclusive prefix sum of the per-Gaussian
-// tile counts (single-pass decoupled look-back), so the op needs no separate scan kernel and no CUB.
-// Streaming, HBM-bound: reads 44 + 12 M bytes, writes 60 bytes per Gaussian.
+// radius, pixel mean, SH -> RGB, opacity-aware pixel AABB, and — fused — a per-block tile histogram (shared-memory
+// atomics, one matrix row per block) that replaces the reference's per-Gaussian prefix sum + host read-back.
+// Streaming, HBM-bound: reads 44 + 12 M bytes, writes 56 bytes per Gaussian.
 //
 // Reference behaviour restated (not copied): the `preprocessCUDA` step of the op called at
 // /root/reference/gs_renderer.py:800-809; maths anchors: gs_renderer.py:85-132 (R, cov3D), sh_utils.py:57-100 (SH).
@@ -130,57 +130,6 @@ __device__ __forceinline__ void project_geo(const FrameConsts &fc, const float3 
     g.cyy = g.T1[0] * ST1[0] + g.T1[1] * ST1[1] + g.T1[2] * ST1[2] + DGR_COV2D_LOWPASS;
 }
 
-// Block-wide exclusive scan of one unsigned per thread + decoupled look-back across blocks (ticket order).
-// Returns this thread's global exclusive prefix; the last block also publishes the grand total.
-__device__ __forceinline__ unsigned long long scan_lookback(unsigned val, unsigned ticket, int nblocks,
-                                                           unsigned long long *status, unsigned long long *total_out) {
-    __shared__ unsigned s_warp[kPreThreads / 32];
-    __shared__ unsigned long long s_block_prefix;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned inc = val;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { unsigned n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    unsigned warp_off = 0, block_total = 0;
-#pragma unroll
-    for (int w = 0; w < kPreThreads / 32; w++) { unsigned v = s_warp[w]; if (w < warp) warp_off += v; block_total += v; }
-    if (warp == 0) {
-        volatile unsigned long long *st = status;
-        const unsigned long long agg = block_total;
-        unsigned long long excl = 0;
-        if (ticket == 0) {
-            if (lane == 0) { st[0] = kFlagPrefix | agg; }
-        } else {
-            if (lane == 0) { st[ticket] = kFlagAggregate | agg; }
-            int base = (int)ticket - 1;
-            while (true) {
-                const int idx = base - lane;
-                const unsigned long long s = (idx >= 0) ? st[idx] : kFlagPrefix;
-                const unsigned flag = (unsigned)(s >> 62);
-                const unsigned m_inv = __ballot_sync(0xffffffffu, flag == 0);
-                const unsigned m_pre = __ballot_sync(0xffffffffu, flag == 2);
-                const int fp = m_pre ? (__ffs(m_pre) - 1) : 32;
-                const unsigned upto = (fp >= 31) ? 0xffffffffu : ((2u << fp) - 1u);
-                if (m_inv & upto) continue;                       // a needed predecessor has not published yet
-                unsigned long long v = (lane <= fp) ? (s & kValueMask) : 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                excl += v;
-                if (fp < 32) break;
-                base -= 32;
-            }
-            if (lane == 0) { __threadfence(); st[ticket] = kFlagPrefix | (excl + agg); }
-        }
-        if (lane == 0) {
-            s_block_prefix = excl;
-            if ((int)ticket == nblocks - 1) *total_out = excl + agg;
-        }
-    }
-    __syncthreads();
-    return s_block_prefix + warp_off + (inc - val);
-}
-
 template <int DEG, bool HAS_SH, bool HAS_COV>
 __global__ void __launch_bounds__(kPreThreads)
 preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, float scale_modifier,
@@ -190,16 +139,17 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                       const float *__restrict__ colors_precomp, const float *__restrict__ opacities,
                       const float *__restrict__ scales, const float *__restrict__ rotations,
                       const float *__restrict__ cov3D_precomp,
-                      int *__restrict__ radii, GeomHeader *__restrict__ hdr, unsigned long long *__restrict__ status,
-                      Rec *__restrict__ rec, unsigned *__restrict__ offsets, unsigned *__restrict__ touched_out,
-                      int nblocks) {
+                      int *__restrict__ radii, Rec *__restrict__ rec, unsigned *__restrict__ touched_out,
+                      unsigned *__restrict__ blk_hist, int tiles, int gpb_iters) {
+    // Per-block tile histogram in shared memory (native integer smem atomics, no global atomics): row `blockIdx.x` of
+    // the [blocks x tiles] matrix that tile_colscan_kernel turns into per-(block, tile) offsets.
+    extern __shared__ unsigned s_hist[];
     __shared__ FrameConsts fc;
-    __shared__ unsigned s_ticket;
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&hdr->ticket, 1u);
     load_frame(fc, viewmatrix, projmatrix, HAS_SH ? campos : nullptr);
+    for (int t = threadIdx.x; t < tiles; t += kPreThreads) s_hist[t] = 0u;
     __syncthreads();
-    const unsigned ticket = s_ticket;
-    const int g = (int)(ticket * kPreThreads + threadIdx.x);
+    for (int it = 0; it < gpb_iters; it++) {
+    const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + threadIdx.x);
     unsigned touched = 0;
     if (g < P) {
         int radius_out = 0;
@@ -272,6 +222,9 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                     }
                     if (bx0 <= bx1 && by0 <= by1) {
                         touched = (unsigned)(((bx1 >> 4) - (bx0 >> 4) + 1) * ((by1 >> 4) - (by0 >> 4) + 1));
+                        // per-tile instance histogram (tile_scan_kernel turns it into ranges)
+                        for (int ty = by0 >> 4; ty <= (by1 >> 4); ty++)
+                            for (int tx = bx0 >> 4; tx <= (bx1 >> 4); tx++) atomicAdd(&s_hist[ty * gx + tx], 1u);
                     } else { bx0 = 1; bx1 = 0; by0 = 1; by1 = 0; }
                     // conic stored as the coefficients of power*log2(e): -0.5 A log2e, -B log2e, -0.5 C log2e
                     r.q0 = make_float4(mx, my, cA * (-0.5f * kLog2e), cB * (-kLog2e));
@@ -284,8 +237,10 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
         rec[g] = r;
         touched_out[g] = touched;
     }
-    const unsigned long long excl = scan_lookback(touched, ticket, nblocks, status, &hdr->n_inst);
-    if (g < P) offsets[g] = (unsigned)excl;
+    }
+    __syncthreads();
+    unsigned *row = blk_hist + (size_t)blockIdx.x * tiles;
+    for (int t = threadIdx.x; t < tiles; t += kPreThreads) row[t] = s_hist[t];
 }
 
 __global__ void mark_visible_kernel(int P, const float *__restrict__ means3D, const float *__restrict__ V, unsigned char *present) {

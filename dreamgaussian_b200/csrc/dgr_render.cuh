@@ -3,13 +3,15 @@
 // B200 design (not the reference's one-thread-per-pixel cooperative fetch):
 //   * a tile's depth-sorted 48-byte records are one contiguous block; one elected thread streams it into shared
 //     memory with 1-D bulk TMA (cp.async.bulk -> UBLKCP) on a 2-stage mbarrier pipeline;
-//   * each warp owns an 8x4 pixel sub-tile.  For every batch of 32 staged records each LANE tests ONE record's
-//     opacity-aware pixel AABB against the warp's sub-tile, the ballot gives the records that can touch the
-//     sub-tile at all, and only those are evaluated (records are broadcast-read from shared memory).  This skips
-//     most of the (pixel, Gaussian) pairs the reference evaluates and then discards at alpha < 1/255;
-//   * backward: per (warp, record) the 10 partial sums are reduced with a 13-shuffle recursive-halving butterfly
-//     (warp-shuffle reduction) and land on 10 lanes which issue ONE red.global.add each — instead of the
-//     reference's ~10 atomics per (pixel, Gaussian) pair.
+//   * each warp owns a sub-tile of 32*PPL pixels (PPL = pixels per lane: 8x4, 8x8 or 16x8).  For every batch of 32
+//     staged records each LANE tests ONE record's opacity-aware pixel AABB against the warp's sub-tile, the ballot gives
+//     the records that can touch the sub-tile at all, and only those are evaluated (records are broadcast-read from
+//     shared memory).  This skips most of the (pixel, Gaussian) pairs the reference evaluates and then discards at
+//     alpha < 1/255;
+//   * tiles are issued heaviest-first (tile_order from the scan kernel), so the long tiles do not form the tail;
+//   * backward: per (warp, record) the 10 partial sums are added over the lane's PPL pixels, reduced over the warp with
+//     a 13-shuffle recursive-halving butterfly (warp-shuffle reduction) and land on 10 lanes which issue ONE
+//     red.global.add each — instead of the reference's ~10 atomics per (pixel, Gaussian) pair.
 // Results follow the reference's rules exactly: power > 0 skip, alpha = min(0.99, o G), alpha < 1/255 skip,
 // stop at T (1 - alpha) < 1e-4, colour + T*bg, un-normalised depth, alpha = sum alpha T.
 #pragma once
@@ -31,20 +33,44 @@ __device__ __forceinline__ bool aabb_hit(unsigned ax, unsigned ay, int wx0, int 
     return (gx0 <= wx1) & (gx1 >= wx0) & (gy0 <= wy1) & (gy1 >= wy0);
 }
 
-__global__ void __launch_bounds__(kTileThreads)
-render_fwd_kernel(int H, int W, int gx, const uint2 *__restrict__ ranges, const Rec *__restrict__ rec_sorted,
-                  const float *__restrict__ bg, float *__restrict__ out_color, float *__restrict__ out_depth,
-                  float *__restrict__ out_alpha, unsigned *__restrict__ n_contrib, float *__restrict__ final_T) {
+// Sub-tile geometry of one warp for PPL pixels per lane.
+template <int PPL>
+struct SubTile {
+    static constexpr int kThreads = kTileThreads / PPL;
+    static constexpr int kW = (PPL == 4) ? 16 : 8;         // region width
+    static constexpr int kH = (PPL == 1) ? 4 : 8;          // region height
+    __device__ static __forceinline__ int x0(int tx, int warp) { return tx * kTile + ((PPL == 4) ? 0 : (warp & 1) * 8); }
+    __device__ static __forceinline__ int y0(int ty, int warp) { return ty * kTile + ((PPL == 4) ? warp * 8 : (warp >> 1) * kH); }
+    __device__ static __forceinline__ int px(int wx0, int lane, int p) { return wx0 + (lane & 7) + ((PPL == 4 && (p & 1)) ? 8 : 0); }
+    __device__ static __forceinline__ int py(int wy0, int lane, int p) { return wy0 + (lane >> 3) + ((PPL == 4) ? (p >> 1) * 4 : p * 4); }
+};
+
+template <int PPL>
+__global__ void __launch_bounds__(kTileThreads / PPL)
+render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const uint2 *__restrict__ ranges,
+                  const Rec *__restrict__ rec_sorted, const float *__restrict__ bg, float *__restrict__ out_color,
+                  float *__restrict__ out_depth, float *__restrict__ out_alpha, unsigned *__restrict__ n_contrib,
+                  float *__restrict__ final_T) {
+    using ST = SubTile<PPL>;
     __shared__ __align__(128) Rec s_rec[2][kChunk];
     __shared__ __align__(8) uint64_t s_bar[2];
-    const int tile = blockIdx.x;
+    const int tile = tile_order ? (int)tile_order[blockIdx.x] : (int)blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wx0 = tx * kTile + (warp & 1) * 8, wy0 = ty * kTile + (warp >> 1) * 4;
-    const int wx1 = wx0 + 7, wy1 = wy0 + 3;
-    const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
-    const bool inside = (px < W) && (py < H);
-    const float fx = (float)px, fy = (float)py;
+    const int wx0 = ST::x0(tx, warp), wy0 = ST::y0(ty, warp);
+    const int wx1 = wx0 + ST::kW - 1, wy1 = wy0 + ST::kH - 1;
+    float fx[PPL], fy[PPL], T[PPL], C0[PPL], C1[PPL], C2[PPL], D[PPL];
+    unsigned last[PPL];
+    bool done[PPL], inside[PPL];
+    bool all_done = true;
+#pragma unroll
+    for (int p = 0; p < PPL; p++) {
+        const int x = ST::px(wx0, lane, p), y = ST::py(wy0, lane, p);
+        inside[p] = (x < W) && (y < H);
+        fx[p] = (float)x; fy[p] = (float)y;
+        T[p] = 1.f; C0[p] = 0.f; C1[p] = 0.f; C2[p] = 0.f; D[p] = 0.f; last[p] = 0; done[p] = !inside[p];
+        all_done = all_done && done[p];
+    }
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
     const int nchunks = (n + kChunk - 1) / kChunk;
@@ -57,21 +83,17 @@ render_fwd_kernel(int H, int W, int gx, const uint2 *__restrict__ ranges, const 
         mbar_expect_tx(&s_bar[0], bytes);
         tma_bulk_g2s(&s_rec[0][0], src, bytes, &s_bar[0]);
     }
-    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
-    unsigned last = 0;
-    bool done = !inside;
     bool warp_done = false;
     int c = 0;
     bool pending_next = false;
     for (; c < nchunks; c++) {
         const int s = c & 1;
-        pending_next = false;
         if (tid == 0 && c + 1 < nchunks) {
             const uint32_t bytes = (uint32_t)min(kChunk, n - (c + 1) * kChunk) * (uint32_t)sizeof(Rec);
             mbar_expect_tx(&s_bar[s ^ 1], bytes);
             tma_bulk_g2s(&s_rec[s ^ 1][0], src + (size_t)(c + 1) * kChunk, bytes, &s_bar[s ^ 1]);
         }
-        if (c + 1 < nchunks) pending_next = true;
+        pending_next = (c + 1 < nchunks);
         mbar_wait(&s_bar[s], (uint32_t)((c >> 1) & 1));
         const int cnt = min(kChunk, n - c * kChunk);
         if (!warp_done) {
@@ -85,40 +107,53 @@ render_fwd_kernel(int H, int W, int gx, const uint2 *__restrict__ ranges, const 
                     mask &= mask - 1;
                     const Rec *r = &s_rec[s][b + j];
                     const float4 q0 = r->q0, q1 = r->q1;
-                    const float dx = q0.x - fx, dy = q0.y - fy;
-                    const float p2 = eval_power2(q0, q1, dx, dy);
-                    const float ag = __fmul_rn(q1.y, ex2_approx(p2));
-                    const float a = fminf(DGR_ALPHA_MAX, ag);
-                    bool ok = (!done) & (p2 <= 0.f) & (a >= DGR_ALPHA_MIN);
-                    const float test_T = __fmul_rn(T, 1.f - a);
-                    if (ok && test_T < DGR_T_STOP) { done = true; ok = false; }
-                    if (ok) {
-                        const float4 q2 = r->q2;
-                        const float w = __fmul_rn(a, T);
-                        C0 = __fmaf_rn(q2.x, w, C0); C1 = __fmaf_rn(q2.y, w, C1); C2 = __fmaf_rn(q2.z, w, C2);
-                        D = __fmaf_rn(q1.z, w, D);
-                        T = test_T;
-                        last = (unsigned)(c * kChunk + b + j + 1);
+                    float4 q2;
+                    bool have_q2 = false;
+#pragma unroll
+                    for (int p = 0; p < PPL; p++) {
+                        const float dx = q0.x - fx[p], dy = q0.y - fy[p];
+                        const float p2 = eval_power2(q0, q1, dx, dy);
+                        const float ag = __fmul_rn(q1.y, ex2_approx(p2));
+                        const float a = fminf(DGR_ALPHA_MAX, ag);
+                        bool ok = (!done[p]) & (p2 <= 0.f) & (a >= DGR_ALPHA_MIN);
+                        const float test_T = __fmul_rn(T[p], 1.f - a);
+                        if (ok && test_T < DGR_T_STOP) { done[p] = true; ok = false; }
+                        if (ok) {
+                            if (!have_q2) { q2 = r->q2; have_q2 = true; }
+                            const float w = __fmul_rn(a, T[p]);
+                            C0[p] = __fmaf_rn(q2.x, w, C0[p]); C1[p] = __fmaf_rn(q2.y, w, C1[p]); C2[p] = __fmaf_rn(q2.z, w, C2[p]);
+                            D[p] = __fmaf_rn(q1.z, w, D[p]);
+                            T[p] = test_T;
+                            last[p] = (unsigned)(c * kChunk + b + j + 1);
+                        }
                     }
                 }
-                if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
+                all_done = true;
+#pragma unroll
+                for (int p = 0; p < PPL; p++) all_done = all_done && done[p];
+                if (__all_sync(0xffffffffu, all_done)) { warp_done = true; break; }
             }
         }
-        const int ndone = __syncthreads_count(done ? 1 : 0);
-        if (ndone == kTileThreads) { c++; break; }
+        const int ndone = __syncthreads_count(all_done ? 1 : 0);
+        if (ndone == ST::kThreads) { c++; break; }
     }
     // never leave the CTA with a bulk copy still in flight into its shared memory
     if (pending_next && c < nchunks && tid == 0) mbar_wait(&s_bar[c & 1], (uint32_t)((c >> 1) & 1));
 
-    if (inside) {
-        const size_t pix = (size_t)py * W + px, HW = (size_t)H * W;
-        out_color[pix] = C0 + T * __ldg(bg);
-        out_color[HW + pix] = C1 + T * __ldg(bg + 1);
-        out_color[2 * HW + pix] = C2 + T * __ldg(bg + 2);
-        out_depth[pix] = D;
-        out_alpha[pix] = 1.f - T;
-        n_contrib[pix] = last;
-        final_T[pix] = T;
+    const float b0 = __ldg(bg), b1 = __ldg(bg + 1), b2 = __ldg(bg + 2);
+    const size_t HW = (size_t)H * W;
+#pragma unroll
+    for (int p = 0; p < PPL; p++) {
+        if (inside[p]) {
+            const size_t pix = (size_t)ST::py(wy0, lane, p) * W + ST::px(wx0, lane, p);
+            out_color[pix] = C0[p] + T[p] * b0;
+            out_color[HW + pix] = C1[p] + T[p] * b1;
+            out_color[2 * HW + pix] = C2[p] + T[p] * b2;
+            out_depth[pix] = D[p];
+            out_alpha[pix] = 1.f - T[p];
+            n_contrib[pix] = last[p];
+            final_T[pix] = T[p];
+        }
     }
 }
 
@@ -147,42 +182,51 @@ __device__ __forceinline__ float reduce12(const float (&v)[12], int lane) {
     return d;
 }
 
-__global__ void __launch_bounds__(kTileThreads)
-render_bwd_kernel(int H, int W, int gx, const uint2 *__restrict__ ranges, const Rec *__restrict__ rec_sorted,
-                  const unsigned *__restrict__ ids_sorted, const float *__restrict__ bg,
+template <int PPL>
+__global__ void __launch_bounds__(kTileThreads / PPL)
+render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const uint2 *__restrict__ ranges,
+                  const Rec *__restrict__ rec_sorted, const unsigned *__restrict__ ids_sorted, const float *__restrict__ bg,
                   const float *__restrict__ final_T, const unsigned *__restrict__ n_contrib,
                   const float *__restrict__ gC, const float *__restrict__ gD, const float *__restrict__ gA,
                   float *__restrict__ grad_rec) {
+    using ST = SubTile<PPL>;
     __shared__ __align__(128) Rec s_rec[2][kChunk];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ unsigned s_maxlast;
-    const int tile = blockIdx.x;
+    const int tile = tile_order ? (int)tile_order[blockIdx.x] : (int)blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wx0 = tx * kTile + (warp & 1) * 8, wy0 = ty * kTile + (warp >> 1) * 4;
-    const int wx1 = wx0 + 7, wy1 = wy0 + 3;
-    const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
-    const bool inside = (px < W) && (py < H);
-    const float fx = (float)px, fy = (float)py;
+    const int wx0 = ST::x0(tx, warp), wy0 = ST::y0(ty, warp);
+    const int wx1 = wx0 + ST::kW - 1, wy1 = wy0 + ST::kH - 1;
     const uint2 range = ranges[tile];
     if (range.y == range.x) return;
 
-    float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, gd = 0.f, ga = 0.f, T = 1.f;
-    unsigned last = 0;
-    if (inside) {
-        const size_t pix = (size_t)py * W + px, HW = (size_t)H * W;
-        last = n_contrib[pix];
-        T = __ldg(final_T + pix);
-        if (gC) { gc0 = __ldg(gC + pix); gc1 = __ldg(gC + HW + pix); gc2 = __ldg(gC + 2 * HW + pix); }
-        if (gD) gd = __ldg(gD + pix);
-        if (gA) ga = __ldg(gA + pix);
+    float fx[PPL], fy[PPL], gc0[PPL], gc1[PPL], gc2[PPL], gd[PPL], ga[PPL], T[PPL], R[PPL];
+    unsigned last[PPL];
+    unsigned lmax = 0;
+    const float b0 = __ldg(bg), b1 = __ldg(bg + 1), b2 = __ldg(bg + 2);
+    const size_t HW = (size_t)H * W;
+#pragma unroll
+    for (int p = 0; p < PPL; p++) {
+        const int x = ST::px(wx0, lane, p), y = ST::py(wy0, lane, p);
+        fx[p] = (float)x; fy[p] = (float)y;
+        gc0[p] = 0.f; gc1[p] = 0.f; gc2[p] = 0.f; gd[p] = 0.f; ga[p] = 0.f; T[p] = 1.f; last[p] = 0;
+        if ((x < W) && (y < H)) {
+            const size_t pix = (size_t)y * W + x;
+            last[p] = n_contrib[pix];
+            T[p] = __ldg(final_T + pix);
+            if (gC) { gc0[p] = __ldg(gC + pix); gc1[p] = __ldg(gC + HW + pix); gc2[p] = __ldg(gC + 2 * HW + pix); }
+            if (gD) gd[p] = __ldg(gD + pix);
+            if (gA) ga[p] = __ldg(gA + pix);
+        }
+        // R = T_final * (bg . gC) + sum over Gaussians behind the current one of w * s
+        R[p] = T[p] * (b0 * gc0[p] + b1 * gc1[p] + b2 * gc2[p]);
+        lmax = max(lmax, last[p]);
     }
-    // R = T_final * (bg . gC) + sum over Gaussians behind the current one of w * s
-    float R = T * (__ldg(bg) * gc0 + __ldg(bg + 1) * gc1 + __ldg(bg + 2) * gc2);
 
     if (tid == 0) { s_maxlast = 0; mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
     __syncthreads();
-    unsigned wmax = last;
+    unsigned wmax = lmax;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
     if (lane == 0 && wmax) atomicMax(&s_maxlast, wmax);
@@ -191,7 +235,7 @@ render_bwd_kernel(int H, int W, int gx, const uint2 *__restrict__ ranges, const 
     const int nchunks = (n + kChunk - 1) / kChunk;
     const Rec *src = rec_sorted + range.x;
     const unsigned *ids = ids_sorted + range.x;
-    unsigned wlast = wmax;                              // warp-level bound
+    const unsigned wlast = wmax;                        // warp-level bound
 
     if (tid == 0 && nchunks > 0) {
         const int c0 = nchunks - 1;
@@ -224,28 +268,42 @@ render_bwd_kernel(int H, int W, int gx, const uint2 *__restrict__ ranges, const 
                     mask &= ~(1u << j);
                     const Rec *r = &s_rec[s][b + j];
                     const float4 q0 = r->q0, q1 = r->q1;
-                    const float dx = q0.x - fx, dy = q0.y - fy;
-                    const float p2 = eval_power2(q0, q1, dx, dy);
-                    const float G = ex2_approx(p2);
-                    const float ag = __fmul_rn(q1.y, G);
-                    const float a = fminf(DGR_ALPHA_MAX, ag);
-                    const bool ok = ((unsigned)(c * kChunk + b + j) < last) & (p2 <= 0.f) & (a >= DGR_ALPHA_MIN);
-                    if (!__any_sync(0xffffffffu, ok)) continue;
+                    const unsigned gidx = (unsigned)(c * kChunk + b + j);
+                    float dxv[PPL], dyv[PPL], agv[PPL], av[PPL];
+                    bool okv[PPL];
+                    bool any_ok = false;
+#pragma unroll
+                    for (int p = 0; p < PPL; p++) {
+                        dxv[p] = q0.x - fx[p]; dyv[p] = q0.y - fy[p];
+                        const float p2 = eval_power2(q0, q1, dxv[p], dyv[p]);
+                        agv[p] = __fmul_rn(q1.y, ex2_approx(p2));
+                        av[p] = fminf(DGR_ALPHA_MAX, agv[p]);
+                        okv[p] = (gidx < last[p]) & (p2 <= 0.f) & (av[p] >= DGR_ALPHA_MIN);
+                        any_ok = any_ok || okv[p];
+                    }
+                    if (!__any_sync(0xffffffffu, any_ok)) continue;
                     float v[12];
 #pragma unroll
                     for (int q = 0; q < 12; q++) v[q] = 0.f;
-                    if (ok) {
+                    if (any_ok) {
                         const float4 q2 = r->q2;
-                        const float ir = rcp_approx(1.f - a);
-                        T = T * ir;
-                        const float sdot = __fmaf_rn(q2.x, gc0, __fmaf_rn(q2.y, gc1, __fmaf_rn(q2.z, gc2, __fmaf_rn(q1.z, gd, ga))));
-                        const float dL_da = T * sdot - R * ir;
-                        const float w = a * T;
-                        R = __fmaf_rn(w, sdot, R);
-                        const float u = ag * dL_da;
-                        v[0] = u; v[1] = u * dx; v[2] = u * dy;
-                        v[3] = v[1] * dx; v[4] = v[1] * dy; v[5] = v[2] * dy;
-                        v[6] = w * gc0; v[7] = w * gc1; v[8] = w * gc2; v[9] = w * gd;
+#pragma unroll
+                        for (int p = 0; p < PPL; p++) {
+                            if (okv[p]) {
+                                const float ir = rcp_approx(1.f - av[p]);
+                                T[p] = T[p] * ir;
+                                const float sdot = __fmaf_rn(q2.x, gc0[p], __fmaf_rn(q2.y, gc1[p], __fmaf_rn(q2.z, gc2[p], __fmaf_rn(q1.z, gd[p], ga[p]))));
+                                const float dL_da = T[p] * sdot - R[p] * ir;
+                                const float w = av[p] * T[p];
+                                R[p] = __fmaf_rn(w, sdot, R[p]);
+                                const float u = agv[p] * dL_da;
+                                const float udx = u * dxv[p], udy = u * dyv[p];
+                                v[0] += u; v[1] += udx; v[2] += udy;
+                                v[3] = __fmaf_rn(udx, dxv[p], v[3]); v[4] = __fmaf_rn(udx, dyv[p], v[4]); v[5] = __fmaf_rn(udy, dyv[p], v[5]);
+                                v[6] = __fmaf_rn(w, gc0[p], v[6]); v[7] = __fmaf_rn(w, gc1[p], v[7]); v[8] = __fmaf_rn(w, gc2[p], v[8]);
+                                v[9] = __fmaf_rn(w, gd[p], v[9]);
+                            }
+                        }
                     }
                     const float red = reduce12(v, lane);
                     const unsigned gid = __shfl_sync(0xffffffffu, my_id, j);

@@ -96,12 +96,16 @@ def _stream_ptr(device):
 
 class ForwardState:
     """Everything one forward leaves behind for its backward (upstream: ctx + geom/binning/img buffers)."""
-    __slots__ = ("rs", "frame", "num_rendered", "geom", "binning", "image", "radii", "alpha", "tensors")
+    __slots__ = ("rs", "frame", "num_rendered", "capacity", "geom", "binning", "image", "radii", "alpha", "tensors")
 
 
 def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D):
     """Runs both forward stages through the C ABI. Inputs are validated CUDA float32 tensors (or None).
-    Returns (color, radii, depth, alpha, ForwardState)."""
+    Returns (color, radii, depth, alpha, ForwardState).
+
+    No host round trip sits between the kernels: the instance buffer is sized from a per-shape capacity hint, every
+    kernel of the forward is enqueued, and only then does the host wait for the (early) instance-count event.  If the
+    guess was too small, stage 2 is re-run with a large enough buffer (the kernels clip safely to the capacity)."""
     lib = _lib.load()
     dev = means3D.device
     with torch.cuda.device(dev):
@@ -112,36 +116,50 @@ def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, 
         depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
         alpha = torch.empty((1, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
-        geom = torch.empty((lib.dgr_geom_bytes(P),), **u8)
+        geom = torch.empty((lib.dgr_geom_bytes(P, H, W),), **u8)
         image = torch.empty((lib.dgr_image_bytes(H, W),), **u8)
-        n_host = _pinned_counter()
+        n_host, event = _host_sync_objects(dev)
         st = _stream_ptr(dev)
-        _lib.check(lib.dgr_forward_preprocess(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(radii),
-                                              ctypes.c_void_p(n_host.data_ptr()), st))
-        torch.cuda.current_stream(dev).synchronize()
-        n_inst = int(n_host[0])
-        binning = torch.empty((lib.dgr_binning_bytes(n_inst, H, W),), **u8) if n_inst > 0 else None
+        _lib.check(lib.dgr_forward_preprocess(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(image),
+                                              _ptr(radii), st))
         out = _lib.DgrImages(_ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii))
-        _lib.check(lib.dgr_forward_render(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(binning),
-                                          ctypes.c_uint64(n_inst), _ptr(image), ctypes.byref(out), st))
+        key = (dev.index, P, H, W)
+        cap = _CAPACITY_HINT.get(key)
+        if cap is None:
+            cap = max(65536, 16 * P)
+        while True:
+            binning = torch.empty((lib.dgr_binning_bytes(cap, H, W),), **u8)
+            _lib.check(lib.dgr_forward_render(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(binning),
+                                              ctypes.c_uint64(cap), _ptr(image), ctypes.byref(out),
+                                              ctypes.c_void_p(n_host.data_ptr()), event, st))
+            _lib.check(lib.dgr_event_synchronize(event))
+            n_inst = int(n_host[0])
+            if n_inst <= cap:
+                break
+            cap = int(n_inst * 1.25) + 4096            # the guess was too small: redo stage 2 (rare)
+        _CAPACITY_HINT[key] = max(int(n_inst * 1.25) + 4096, 65536)
     state = ForwardState()
-    state.rs, state.frame, state.num_rendered = rs, fr, n_inst
+    state.rs, state.frame, state.num_rendered, state.capacity = rs, fr, n_inst, cap
     state.geom, state.binning, state.image, state.radii, state.alpha = geom, binning, image, radii, alpha
     state.tensors = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3D)
     return color, radii, depth, alpha, state
 
 
-_PINNED = {}
+_SYNC = {}
+_CAPACITY_HINT = {}
 
 
-def _pinned_counter():
-    """One pinned uint64 per host thread for the instance-count read-back."""
+def _host_sync_objects(dev):
+    """(pinned uint64 for the instance count, cudaEvent handle) per (host thread, device)."""
     import threading
-    key = threading.get_ident()
-    t = _PINNED.get(key)
+    key = (threading.get_ident(), dev.index)
+    t = _SYNC.get(key)
     if t is None:
-        t = torch.zeros((1,), dtype=torch.int64).pin_memory()
-        _PINNED[key] = t
+        ev = _lib.load().dgr_event_create()
+        if not ev:
+            raise RuntimeError("libdgr_b200: could not create a CUDA event")
+        t = (torch.zeros((1,), dtype=torch.int64).pin_memory(), ctypes.c_void_p(ev))
+        _SYNC[key] = t
     return t
 
 
@@ -156,7 +174,7 @@ def backward_impl(state, grad_color, grad_depth, grad_alpha, d_means3D, d_means2
         gout = _lib.DgrGaussianGrads(_ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh), _ptr(d_col), _ptr(d_opac), _ptr(d_scales),
                                      _ptr(d_rot), _ptr(d_cov), 1 if accumulate else 0)
         _lib.check(lib.dgr_backward(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(state.geom), _ptr(state.binning),
-                                    ctypes.c_uint64(state.num_rendered), _ptr(state.image), _ptr(state.radii), _ptr(state.alpha),
+                                    ctypes.c_uint64(state.capacity), _ptr(state.image), _ptr(state.radii), _ptr(state.alpha),
                                     ctypes.byref(gin), ctypes.byref(gout), _stream_ptr(dev)))
 
 

@@ -83,22 +83,34 @@ typedef struct DgrGaussianGrads {
 
 /* Scratch sizes.  The caller owns the three scratch buffers (upstream: geomBuffer / binningBuffer / imgBuffer),
  * must keep them alive and untouched between a forward and its backward, and aligns them to 256 bytes. */
-size_t dgr_geom_bytes(int32_t P);
+size_t dgr_geom_bytes(int32_t P, int32_t image_height, int32_t image_width);
 size_t dgr_image_bytes(int32_t image_height, int32_t image_width);
 size_t dgr_binning_bytes(uint64_t capacity_instances, int32_t image_height, int32_t image_width);
 
-/* Forward, stage 1: per-Gaussian preprocess (cull, EWA cov2D, conic, radius, SH->RGB) + instance count.
- * Writes radii.  The number of tile instances is written to geom scratch and, if n_instances_host != NULL
- * (pinned host memory), copied there asynchronously on `stream` (uint64). */
-int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *geom, int32_t *radii,
-                           uint64_t *n_instances_host, void *stream);
+/* Forward, stage 1: per-Gaussian preprocess (cull, EWA cov2D, conic, radius, SH->RGB, opacity-aware pixel AABB)
+ * fused with the per-tile instance histogram (kept in `image` scratch).  Writes radii. */
+int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *geom, void *image, int32_t *radii,
+                           void *stream);
 
-/* Forward, stage 2: tile binning + depth sort + per-tile front-to-back compositing.
- * `capacity_instances` is the instance capacity `binning` was sized for; if the true count exceeds it the
- * call renders a truncated instance list and the caller must re-run stage 2 with a larger buffer
- * (compare *n_instances_host with the capacity after the stream has passed stage 1). */
+/* Forward, stage 2: tile ranges (device-side scan), instance emission, per-tile depth sort + record gather, and the
+ * per-tile front-to-back compositing.  Nothing here waits for the host: `capacity_instances` is the instance capacity
+ * `binning` was sized for (a guess is fine).  The true instance count is written to geom scratch and, if
+ * n_instances_host != NULL (pinned host memory), copied there asynchronously right after the scan; if
+ * count_ready_event != NULL (from dgr_event_create) it is recorded at that point, so the caller can keep enqueuing
+ * work and check `*n_instances_host <= capacity_instances` once that event has fired.  If the count exceeds the
+ * capacity the call rendered a truncated (but memory-safe) instance list: re-run stage 2 with a larger buffer. */
 int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom, void *binning,
-                       uint64_t capacity_instances, void *image, const DgrImages *out, void *stream);
+                       uint64_t capacity_instances, void *image, const DgrImages *out,
+                       uint64_t *n_instances_host, void *count_ready_event, void *stream);
+
+/* Tuning knobs (process-wide; results do not depend on them): pixels per lane of the forward / backward render
+ * kernels (1, 2 or 4) and whether tiles are issued heaviest-first (1) or in row-major order (0). */
+int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order);
+
+/* Thin cudaEvent wrappers so a host without the CUDA runtime headers (ctypes, cgo ...) can use the protocol above. */
+void *dgr_event_create(void);
+int dgr_event_synchronize(void *event);
+void dgr_event_destroy(void *event);
 
 /* Backward of both stages.  geom / binning / image are the scratch buffers of the matching forward
  * (`capacity_instances` = the value stage 2 ran with); geom is also used as scratch for the per-Gaussian
@@ -114,7 +126,7 @@ int dgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, c
 
 /* Introspection for tests: copies per-Gaussian forward state out of geom scratch (any pointer may be NULL):
  * mean_px [P,2], depth [P], conic [P,3] (natural units), rgb [P,3], opacity-aware pixel AABB [P,4] int32. */
-int dgr_debug_geom(int32_t P, const void *geom, float *mean_px, float *depth, float *conic, float *rgb,
+int dgr_debug_geom(int32_t P, int32_t image_height, int32_t image_width, const void *geom, float *mean_px, float *depth, float *conic, float *rgb,
                    int32_t *aabb, uint32_t *tiles_touched, void *stream);
 
 /* How many kernels of THIS library were launched by the calling thread since the last reset (for bench.py). */

@@ -16,13 +16,21 @@ def main():
         ("big_gauss", dict(P=500, res=80, deg=2, sigma=0.2, elev=25, azim=-100)),
         ("mid_20k_400", dict(P=20000, res=400, deg=3)),
     ]
+    cases += [
+        ("big_tiles_radix", dict(P=20000, res=32, deg=0, sigma=0.02)),            # ~5k instances per tile: big-list radix path
+        ("huge_tiles_bitonic", dict(P=60000, res=32, deg=0, sigma=0.01)),         # > 11264 per tile: in-place global network
+        ("planar_equal_depth", dict(P=3000, res=64, deg=1, sigma=0.03, planar=True)),  # all depths equal: degenerate-run fallback
+    ]
     if "--tiny" in sys.argv:
         cases = cases[:3]
     if "--full" in sys.argv:
         cases.append(("cfg2_100k_800", dict(P=100000, res=800, deg=3)))
     allrep = {}
     for name, kw in cases:
+        planar = kw.pop("planar", False)
         s, i = h.make_case(**kw)
+        if planar:      # squash the cloud onto the plane z = 0 seen head-on: every Gaussian has the same view depth
+            i["means3D"] = i["means3D"].copy(); i["means3D"][:, 2] = 0.0
         g = h.upstream_grads(s["image_height"], s["image_width"])
         t0 = time.time(); ref = h.run_oracle(s, i, g); t1 = time.time()
         try:

@@ -90,7 +90,8 @@ int check_gaussians(const DgrSettings *s, const DgrGaussians *g) {
 constexpr size_t kMaxTileSmem = 200 * 1024;      // tile-histogram rows live in shared memory: up to 51200 tiles
 
 template <int DEG, bool HAS_SH, bool HAS_COV>
-void launch_pre_fwd(const DgrSettings *s, const DgrGaussians *g, int *radii, char *geom, const GeomLayout &L, cudaStream_t st) {
+void launch_pre_fwd(const DgrSettings *s, const DgrGaussians *g, int *radii, char *geom, const GeomLayout &L, unsigned *colscan_done,
+                    cudaStream_t st) {
     const size_t smem = (size_t)L.tiles * 4;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -98,7 +99,7 @@ void launch_pre_fwd(const DgrSettings *s, const DgrGaussians *g, int *radii, cha
         g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
         s->campos, g->means3D, g->shs, g->colors_precomp, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii,
         reinterpret_cast<Rec *>(geom + L.off_rec), reinterpret_cast<unsigned *>(geom + L.off_touched),
-        reinterpret_cast<unsigned *>(geom + L.off_blkhist), L.tiles, L.iters);
+        reinterpret_cast<unsigned *>(geom + L.off_blkhist), L.tiles, L.iters, colscan_done);
 }
 
 template <int DEG, bool HAS_SH, bool HAS_COV>
@@ -143,7 +144,7 @@ __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched
 bool g_sort_attr_set = false;
 int g_big_grid = 148;
 // tuning knobs (dgr_set_tuning): pixels per lane of the render kernels, heaviest-first tile order on/off
-int g_ppl_fwd = 1, g_ppl_bwd = 1;
+int g_ppl_fwd = 1, g_ppl_bwd = 2;
 bool g_no_order = false;
 bool g_emit_attr_set = false;
 }  // namespace
@@ -199,21 +200,25 @@ int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *ge
     if (int e = check_settings(s)) return e;
     if (int e = check_gaussians(s, g)) return e;
     cudaStream_t st = (cudaStream_t)stream;
-    char *geom = (char *)geom_v;
-    if (!geom || !image_v) return fail(-1, "geom / image scratch is NULL");
+    char *geom = (char *)geom_v, *image = (char *)image_v;
+    if (!geom || !image) return fail(-1, "geom / image scratch is NULL");
     GeomLayout L(g->P, s->image_height, s->image_width);
+    ImageLayout IL(s->image_height, s->image_width);
     if ((size_t)L.tiles * 4 > kMaxTileSmem) return fail(-3, "image has more than 51200 tiles (16x16): not supported");
+    TileWork *work = reinterpret_cast<TileWork *>(image + IL.off_work);
     if (g->P > 0) {
         if (!radii) return fail(-1, "radii is NULL");
-        DGR_KERNEL("preprocess_fwd", st, s->debug, DGR_DISPATCH(launch_pre_fwd, s, g, radii, geom, L, st));
+        DGR_KERNEL("preprocess_fwd", st, s->debug, DGR_DISPATCH(launch_pre_fwd, s, g, radii, geom, L, &work->done, st));
     } else {
         DGR_CUDA(cudaMemsetAsync(geom + L.off_blkhist, 0, (size_t)L.nblocks * L.tiles * 4, st));
+        DGR_CUDA(cudaMemsetAsync(work, 0, sizeof(TileWork), st));
     }
     return 0;
 }
 
 int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v, void *binning_v, uint64_t capacity,
-                       void *image_v, const DgrImages *out, uint64_t *n_instances_host, void *count_ready_event, void *stream) {
+                       void *image_v, const DgrImages *out, int32_t flags, uint64_t *counts_host, void *count_ready_event,
+                       void *stream) {
     if (int e = check_settings(s)) return e;
     if (!g || !geom_v || !image_v || !out) return fail(-1, "NULL argument");
     if (!out->color || !out->depth || !out->alpha) return fail(-1, "output images must not be NULL");
@@ -238,15 +243,14 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
     unsigned *ids = binning ? reinterpret_cast<unsigned *>(binning + BL.off_ids) : nullptr;
     Rec *recs = binning ? reinterpret_cast<Rec *>(binning + BL.off_rec) : nullptr;
 
-    DGR_KERNEL("tile_colscan", st, s->debug,
-               tile_colscan_kernel<<<(tiles + 31) / 32, 1024, 0, st>>>(tiles, GL.nblocks, blk_hist, tile_count));
     unsigned *tile_order = reinterpret_cast<unsigned *>(image + IL.off_order);
     unsigned *big_list = reinterpret_cast<unsigned *>(image + IL.off_biglist);
     TileWork *work = reinterpret_cast<TileWork *>(image + IL.off_work);
-    DGR_KERNEL("tile_scan", st, s->debug,
-               tile_scan_kernel<<<1, 1024, 0, st>>>(tiles, tile_count, (unsigned long long)capacity, ranges, hdr, tile_order, work, big_list));
-    if (n_instances_host)
-        DGR_CUDA(cudaMemcpyAsync(n_instances_host, geom, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    DGR_KERNEL("tile_colscan_scan", st, s->debug,
+               tile_colscan_kernel<<<(tiles + 31) / 32, 1024, 0, st>>>(tiles, GL.nblocks, blk_hist, tile_count, (unsigned long long)capacity,
+                                                                        ranges, hdr, tile_order, work, big_list));
+    if (counts_host)      // { n_instances, n_big_tiles }
+        DGR_CUDA(cudaMemcpyAsync(counts_host, geom, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     if (count_ready_event) DGR_CUDA(cudaEventRecord((cudaEvent_t)count_ready_event, st));
     if (g->P > 0 && capacity > 0) {
         const size_t smem = (size_t)tiles * 4;
@@ -257,8 +261,8 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
         DGR_KERNEL("emit_instances", st, s->debug,
                    emit_instances_kernel<<<GL.nblocks, kPreThreads, smem, st>>>(
                        g->P, IL.gx, tiles, GL.iters, rec, reinterpret_cast<const unsigned *>(geom + GL.off_touched), ranges, blk_hist, keys));
-        using SmS = SortSmem<kSortSmallThreads, kSortSmallCap>;
-        using SmB = SortSmem<kSortBigThreads, kSortBigCap>;
+        using SmS = SortSmem<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>;
+        using SmB = SortSmem<kSortBigThreads, kSortBigCap, kSortBigBuckets>;
         if (!g_sort_attr_set) {
             DGR_CUDA(cudaFuncSetAttribute(tile_sort_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmS::bytes));
             DGR_CUDA(cudaFuncSetAttribute(tile_sort_gather_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmB::bytes));
@@ -266,13 +270,14 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
         }
         DGR_KERNEL("tile_sort_gather", st, s->debug,
                    tile_sort_gather_kernel<<<tiles, kSortSmallThreads, SmS::bytes, st>>>(tile_order, ranges, keys, rec, ids, recs));
-        DGR_KERNEL("tile_sort_gather_big", st, s->debug,
-                   tile_sort_gather_big_kernel<<<g_big_grid, kSortBigThreads, SmB::bytes, st>>>(work, big_list, ranges, keys, rec, ids, recs));
+        if (flags & DGR_FLAG_BIG_TILES)
+            DGR_KERNEL("tile_sort_gather_big", st, s->debug,
+                       tile_sort_gather_big_kernel<<<g_big_grid, kSortBigThreads, SmB::bytes, st>>>(work, big_list, ranges, keys, rec, ids, recs));
     }
     const unsigned *render_order = g_no_order ? nullptr : tile_order;
 #define DGR_RENDER_FWD(PPL_)                                                                                   \
     DGR_KERNEL("render_fwd", st, s->debug,                                                                      \
-               render_fwd_kernel<PPL_><<<(unsigned)tiles, kTileThreads / PPL_, 0, st>>>(                        \
+               render_fwd_kernel<PPL_><<<(unsigned)tiles, SubTile<PPL_>::kThreads, 0, st>>>(                        \
                    H, W, IL.gx, render_order, ranges, recs, s->bg, out->color, out->depth, out->alpha, n_contrib, final_T))
     if (g_ppl_fwd == 4) DGR_RENDER_FWD(4); else if (g_ppl_fwd == 2) DGR_RENDER_FWD(2); else DGR_RENDER_FWD(1);
 #undef DGR_RENDER_FWD
@@ -302,7 +307,7 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
         const unsigned *tile_order = g_no_order ? nullptr : reinterpret_cast<const unsigned *>(image + IL.off_order);
 #define DGR_RENDER_BWD(PPL_)                                                                                              \
     DGR_KERNEL("render_bwd", st, s->debug,                                                                                 \
-               render_bwd_kernel<PPL_><<<(unsigned)tiles, kTileThreads / PPL_, 0, st>>>(                                   \
+               render_bwd_kernel<PPL_><<<(unsigned)tiles, SubTile<PPL_>::kThreads, 0, st>>>(                                   \
                    H, W, IL.gx, tile_order, reinterpret_cast<const uint2 *>(image + IL.off_ranges),                        \
                    reinterpret_cast<const Rec *>(binning + BL.off_rec), reinterpret_cast<const unsigned *>(binning + BL.off_ids), \
                    s->bg, reinterpret_cast<const float *>(image + IL.off_finalT),                                          \

@@ -31,39 +31,6 @@ struct BinningLayout {
     }
 };
 
-// Column scan of the [nblocks x tiles] count matrix (in place -> exclusive per-(block, tile) offsets) + column totals.
-// One CTA = 32 tiles (lanes, coalesced 128-byte rows) x 32 block-groups (warps): every thread first sums its slice of
-// the column, the 32 partial sums are scanned through shared memory, then the slice is rewritten as running offsets.
-__global__ void __launch_bounds__(1024)
-tile_colscan_kernel(int tiles, int nblocks, unsigned *__restrict__ blk_hist, unsigned *__restrict__ tile_count) {
-    __shared__ unsigned s_part[32][33];
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const int t = blockIdx.x * 32 + lane;
-    const int per = (nblocks + 31) / 32;
-    const int b0 = grp * per, b1 = min(nblocks, b0 + per);
-    unsigned sum = 0;
-    if (t < tiles) {
-        const unsigned *p = blk_hist + t;
-#pragma unroll 4
-        for (int b = b0; b < b1; b++) sum += p[(size_t)b * tiles];
-    }
-    s_part[grp][lane] = sum;
-    __syncthreads();
-    if (grp == 0) {                       // one warp: exclusive scan over the 32 groups of each tile (lane = tile)
-        unsigned run = 0;
-#pragma unroll
-        for (int g = 0; g < 32; g++) { const unsigned v = s_part[g][lane]; s_part[g][lane] = run; run += v; }
-        if (t < tiles) tile_count[t] = run;
-    }
-    __syncthreads();
-    if (t < tiles) {
-        unsigned run = s_part[grp][lane];
-        unsigned *p = blk_hist + t;
-#pragma unroll 4
-        for (int b = b0; b < b1; b++) { const unsigned c = p[(size_t)b * tiles]; p[(size_t)b * tiles] = run; run += c; }
-    }
-}
-
 __device__ __forceinline__ void cmpex(unsigned long long *a, int i, int l) {
     const unsigned long long x = a[i], y = a[l];
     if (x > y) { a[i] = y; a[l] = x; }
@@ -98,9 +65,10 @@ __device__ __forceinline__ void bitonic_sort_cta(unsigned long long *a, int n) {
 constexpr int kSortSmallCap = 4096;
 constexpr int kOrderBins = 128;          // log-scale population classes for the heaviest-first issue order
 
-struct TileWork {                        // written by tile_scan_kernel (lives in image scratch)
-    unsigned n_big;                      // number of entries of big_list
-    unsigned pad[3];
+struct TileWork {                        // lives in image scratch
+    unsigned n_big;                      // number of entries of big_list (written by the tile scan)
+    unsigned done;                       // CTAs of tile_colscan_kernel that have finished (zeroed by the preprocess kernel)
+    unsigned pad[2];
 };
 
 __device__ __forceinline__ int order_bin(unsigned count) {
@@ -115,10 +83,10 @@ __device__ __forceinline__ int order_bin(unsigned count) {
 // One CTA: exclusive scan of the per-tile instance counts -> ranges (clipped to `cap`), total -> header; plus the
 // heaviest-first issue order of the render kernels (counting sort on log-scale population classes — longest
 // processing time first keeps the big tiles off the tail) and the list of tiles too big for the per-tile sort CTA.
-__global__ void __launch_bounds__(1024)
-tile_scan_kernel(int tiles, const unsigned *__restrict__ tile_count, unsigned long long cap, uint2 *__restrict__ ranges,
-                 GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order, TileWork *__restrict__ work,
-                 unsigned *__restrict__ big_list) {
+__device__ __forceinline__ void
+tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long long cap, uint2 *__restrict__ ranges,
+              GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order, TileWork *__restrict__ work,
+              unsigned *__restrict__ big_list) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_carry, s_total;
     __shared__ unsigned s_bin[kOrderBins], s_nbig;
@@ -128,7 +96,7 @@ tile_scan_kernel(int tiles, const unsigned *__restrict__ tile_count, unsigned lo
     __syncthreads();
     for (int base = 0; base < tiles; base += 1024) {
         const int t = base + tid;
-        const unsigned long long v = (t < tiles) ? tile_count[t] : 0u;
+        const unsigned long long v = (t < tiles) ? __ldcg(tile_count + t) : 0u;
         unsigned long long inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
@@ -155,7 +123,7 @@ tile_scan_kernel(int tiles, const unsigned *__restrict__ tile_count, unsigned lo
         if (tid == 0) s_carry += s_total;
         __syncthreads();
     }
-    if (tid == 0) { hdr->n_inst = s_carry; work->n_big = s_nbig; }
+    if (tid == 0) { hdr->n_inst = s_carry; hdr->n_big = s_nbig; work->n_big = s_nbig; }
     // counting sort of the tiles by population class
     if (warp == 0) {
         unsigned run = 0;
@@ -172,6 +140,52 @@ tile_scan_kernel(int tiles, const unsigned *__restrict__ tile_count, unsigned lo
     for (int t = tid; t < tiles; t += 1024) {
         const uint2 r = ranges[t];
         tile_order[atomicAdd(&s_bin[order_bin(r.y - r.x)], 1u)] = (unsigned)t;
+    }
+}
+
+// Column scan of the [nblocks x tiles] count matrix (in place -> exclusive per-(block, tile) offsets) + column totals.
+// One CTA = 32 tiles (lanes, coalesced 128-byte rows) x 32 block-groups (warps): every thread first sums its slice of
+// the column, the 32 partial sums are scanned through shared memory, then the slice is rewritten as running offsets.
+__global__ void __launch_bounds__(1024)
+tile_colscan_kernel(int tiles, int nblocks, unsigned *__restrict__ blk_hist, unsigned *__restrict__ tile_count,
+                    unsigned long long cap, uint2 *__restrict__ ranges, GeomHeader *__restrict__ hdr,
+                    unsigned *__restrict__ tile_order, TileWork *__restrict__ work, unsigned *__restrict__ big_list) {
+    __shared__ unsigned s_part[32][33];
+    __shared__ unsigned s_ticket;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
+    const int per = (nblocks + 31) / 32;
+    const int b0 = grp * per, b1 = min(nblocks, b0 + per);
+    unsigned sum = 0;
+    if (t < tiles) {
+        const unsigned *p = blk_hist + t;
+#pragma unroll 4
+        for (int b = b0; b < b1; b++) sum += p[(size_t)b * tiles];
+    }
+    s_part[grp][lane] = sum;
+    __syncthreads();
+    if (grp == 0) {                       // one warp: exclusive scan over the 32 groups of each tile (lane = tile)
+        unsigned run = 0;
+#pragma unroll
+        for (int g = 0; g < 32; g++) { const unsigned v = s_part[g][lane]; s_part[g][lane] = run; run += v; }
+        if (t < tiles) tile_count[t] = run;
+    }
+    __syncthreads();
+    if (t < tiles) {
+        unsigned run = s_part[grp][lane];
+        unsigned *p = blk_hist + t;
+#pragma unroll 4
+        for (int b = b0; b < b1; b++) { const unsigned c = p[(size_t)b * tiles]; p[(size_t)b * tiles] = run; run += c; }
+    }
+    // the last CTA to finish turns the column totals into tile ranges (saves a launch and its round trip)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&work->done, 1u);
+    __syncthreads();
+    if (s_ticket == gridDim.x - 1) {
+        __threadfence();
+        tile_scan_cta(tiles, tile_count, cap, ranges, hdr, tile_order, work, big_list);
+        if (threadIdx.x == 0) work->done = 0u;          // ready for a re-run of stage 2 with a larger capacity
     }
 }
 
@@ -204,94 +218,36 @@ emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, const Rec *__rest
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// Per-tile sort by (depth, Gaussian id) + record gather.
+// Per-tile sort by (depth, Gaussian id) + record gather: bucket + rank.
 //
-// Sorting 64-bit keys with a comparison network costs O(n log^2 n) shared-memory compare-exchanges; instead each tile
-// quantises its depths to 16 bits over ITS OWN [min, max] depth range (monotone), runs a stable 2-pass LSD radix sort
-// (8-bit digits, warp match.any ranking) on 32-bit (q16 << 16 | index) items, and then repairs the few runs of equal
-// q16 by comparing the full 64-bit keys.  The result is exactly the (depth, id) order — the reference's stable
-// (tile, depth) order — at ~100 instructions per key.  Degenerate inputs (a long run of equal quantised depth, e.g. a
-// planar cloud seen head-on) fall back to the bitonic network on the full keys.
+// A comparison network costs O(n log^2 n) dependent shared-memory round trips and ~20 block barriers; a multi-pass
+// radix sort needs ordered (stable) ranking.  Neither is necessary: the keys are unique, so an element's final
+// position is simply (start of its bucket) + (number of smaller keys in its bucket).  Each tile
+//   1. loads its 64-bit keys and finds its own [min, max] depth,
+//   2. drops every key into one of NB equal-width depth buckets (monotone in depth) with shared-memory integer
+//      atomics — the order inside a bucket is arbitrary,
+//   3. ranks every key inside its bucket by brute-force counting with the FULL (depth, id) key,
+//   4. writes the Gaussian id and gathers the 48-byte record straight to the sorted position.
+// Four block barriers, no serial phases, ~60 instructions per key for any reasonable depth distribution; a degenerate
+// one (many equal depths, e.g. a planar cloud seen head-on) only makes step 3 longer — it stays exact: the result is
+// the (depth, id) order, i.e. the reference's stable (tile, depth) order.
 // ----------------------------------------------------------------------------------------------------------------
-template <int THREADS, int CAP>
+template <int THREADS, int CAP, int NBK>
 struct SortSmem {
-    static constexpr int kWarps = THREADS / 32;
-    static constexpr size_t off_keys = 0;                                   // u64 [CAP]
-    static constexpr size_t off_i0 = off_keys + (size_t)CAP * 8;            // u32 [CAP]
-    static constexpr size_t off_i1 = off_i0 + (size_t)CAP * 4;              // u32 [CAP]
-    static constexpr size_t off_cnt = off_i1 + (size_t)CAP * 4;             // u16 [kWarps][256]
-    static constexpr size_t off_base = off_cnt + (size_t)kWarps * 256 * 2;  // u32 [256]
-    static constexpr size_t off_misc = off_base + 256 * 4;                  // u32 [8 + kWarps * 2]
-    static constexpr size_t bytes = off_misc + (8 + kWarps * 2) * 4;
+    static constexpr size_t off_a = 0;                                       // u64 [CAP]  keys as loaded
+    static constexpr size_t off_b = off_a + (size_t)CAP * 8;                 // u64 [CAP]  keys grouped by bucket
+    static constexpr size_t off_start = off_b + (size_t)CAP * 8;             // u32 [NBK + 1] bucket starts
+    static constexpr size_t off_cur = off_start + (NBK + 32) * 4;   // u32 [NBK]     scatter cursors
+    static constexpr size_t off_misc = off_cur + NBK * 4;           // u32 [64]
+    static constexpr size_t bytes = off_misc + 64 * 4;
 };
 
-template <int THREADS>
-__device__ __forceinline__ void radix_pass(const unsigned *__restrict__ src, unsigned *__restrict__ dst, int n, int shift,
-                                           unsigned short *cnt /*[W][256]*/, unsigned *base /*[256]*/) {
-    constexpr int W = THREADS / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int seg = ((n + W - 1) / W + 31) & ~31;                          // items per warp, multiple of 32
-    const int w0 = warp * seg, w1 = min(n, w0 + seg);
-    for (int i = tid; i < W * 256; i += THREADS) cnt[i] = 0;
-    __syncthreads();
-    unsigned short *mycnt = cnt + warp * 256;
-    for (int e = w0 + lane; e - lane < w1; e += 32) {                       // warp-uniform trip count
-        const bool valid = e < w1;
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const unsigned d = (src[e] >> shift) & 0xffu;
-            const unsigned peers = __match_any_sync(act, d);
-            if ((unsigned)lane == (unsigned)(__ffs(peers) - 1)) mycnt[d] = (unsigned short)(mycnt[d] + __popc(peers));
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-    // digit totals and per-warp exclusive prefixes: thread d (< 256) owns digit d
-    unsigned total = 0;
-    if (tid < 256) {
-#pragma unroll 4
-        for (int w = 0; w < W; w++) { const unsigned c = cnt[w * 256 + tid]; cnt[w * 256 + tid] = (unsigned short)total; total += c; }
-    }
-    // exclusive scan of the 256 totals (threads 0..255 = 8 warps)
-    unsigned inc = total;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-    __shared__ unsigned s_wsum[8];
-    if (tid < 256 && lane == 31) s_wsum[warp] = inc;
-    __syncthreads();
-    if (tid < 256) {
-        unsigned off = 0;
-#pragma unroll
-        for (int w = 0; w < 8; w++) if (w < warp) off += s_wsum[w];
-        base[tid] = off + inc - total;
-    }
-    __syncthreads();
-    for (int e = w0 + lane; e - lane < w1; e += 32) {
-        const bool valid = e < w1;
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        unsigned d = 0, peers = 0, item = 0, pos = 0;
-        if (valid) {
-            item = src[e];
-            d = (item >> shift) & 0xffu;
-            peers = __match_any_sync(act, d);
-            pos = base[d] + mycnt[d] + __popc(peers & ((1u << lane) - 1u));
-        }
-        __syncwarp();
-        if (valid) {
-            dst[pos] = item;
-            if ((unsigned)lane == (unsigned)(__ffs(peers) - 1)) mycnt[d] = (unsigned short)(mycnt[d] + __popc(peers));
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-}
-
-template <int THREADS, int CAP>
+template <int THREADS, int CAP, int NBK>
 __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long long *__restrict__ keys, const Rec *__restrict__ rec,
                                                  unsigned *__restrict__ ids_sorted, Rec *__restrict__ rec_sorted, unsigned char *smem) {
-    using SM = SortSmem<THREADS, CAP>;
+    using SM = SortSmem<THREADS, CAP, NBK>;
     const int n = (int)(r.y - r.x);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     unsigned long long *gk = keys + r.x;
     if (n > CAP) {                                     // beyond the shared-memory capacity: in-place network in global memory
         __syncthreads();
@@ -306,12 +262,16 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
         __syncthreads();
         return;
     }
-    unsigned long long *A = reinterpret_cast<unsigned long long *>(smem + SM::off_keys);
-    unsigned *I0 = reinterpret_cast<unsigned *>(smem + SM::off_i0), *I1 = reinterpret_cast<unsigned *>(smem + SM::off_i1);
-    unsigned short *cnt = reinterpret_cast<unsigned short *>(smem + SM::off_cnt);
-    unsigned *base = reinterpret_cast<unsigned *>(smem + SM::off_base);
-    unsigned *misc = reinterpret_cast<unsigned *>(smem + SM::off_misc);     // [0] min bits, [1] max bits, [2] long-run flag
-    if (tid == 0) { misc[0] = 0xffffffffu; misc[1] = 0u; misc[2] = 0u; }
+    unsigned long long *A = reinterpret_cast<unsigned long long *>(smem + SM::off_a);
+    unsigned long long *B = reinterpret_cast<unsigned long long *>(smem + SM::off_b);
+    unsigned *start = reinterpret_cast<unsigned *>(smem + SM::off_start);
+    unsigned *cur = reinterpret_cast<unsigned *>(smem + SM::off_cur);
+    unsigned *misc = reinterpret_cast<unsigned *>(smem + SM::off_misc);     // [0] min bits, [1] max bits, [2..] warp sums
+    // bucket count: a power of two near n/2 (about two keys per bucket for a uniform spread)
+    int nb = 64;
+    while (nb < NBK && nb * 2 <= n) nb <<= 1;
+    if (tid == 0) { misc[0] = 0xffffffffu; misc[1] = 0u; }
+    for (int i = tid; i < nb; i += THREADS) cur[i] = 0u;
     __syncthreads();
     unsigned lo = 0xffffffffu, hi = 0u;
     for (int i = tid; i < n; i += THREADS) {
@@ -322,59 +282,64 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
-    if ((tid & 31) == 0) { atomicMin(&misc[0], lo); atomicMax(&misc[1], hi); }
+    if (lane == 0) { atomicMin(&misc[0], lo); atomicMax(&misc[1], hi); }
     __syncthreads();
-    if (n > 1) {
-        const float dmin = __uint_as_float(misc[0]), dmax = __uint_as_float(misc[1]);
-        const float scale = (dmax > dmin) ? 65535.f / (dmax - dmin) : 0.f;
-        for (int i = tid; i < n; i += THREADS) {
-            const float d = __uint_as_float((unsigned)(A[i] >> 32));
-            const unsigned q = min(65535u, (unsigned)((d - dmin) * scale));          // monotone in d
-            I0[i] = (q << 16) | (unsigned)i;
-        }
-        __syncthreads();
-        radix_pass<THREADS>(I0, I1, n, 16, cnt, base);
-        radix_pass<THREADS>(I1, I0, n, 24, cnt, base);
-        // repair runs of equal q16 with the full (depth, id) keys; each run is owned by the thread of its first element
-        for (int i = tid; i < n; i += THREADS) {
-            const unsigned q = I0[i] >> 16;
-            if ((i == 0 || (I0[i - 1] >> 16) != q) && (i + 1 < n) && (I0[i + 1] >> 16) == q) {
-                int e = i + 2;
-                while (e < n && (I0[e] >> 16) == q && e - i <= 16) e++;
-                if (e - i > 16) { misc[2] = 1u; }
-                else {
-                    for (int a = i + 1; a < e; a++) {                                  // insertion sort of the run
-                        const unsigned it = I0[a];
-                        const unsigned long long ka = A[it & 0xffffu];
-                        int b = a - 1;
-                        while (b >= i && A[I0[b] & 0xffffu] > ka) { I0[b + 1] = I0[b]; b--; }
-                        I0[b + 1] = it;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        if (misc[2]) {                                  // degenerate depth distribution: comparison network on the full keys
-            bitonic_sort_cta(A, n);
-            for (int i = tid; i < n; i += THREADS) I0[i] = (unsigned)i;
-            __syncthreads();
-        }
-    } else {
-        if (tid == 0) I0[0] = 0u;
-        __syncthreads();
-    }
+    const float dmin = __uint_as_float(misc[0]), dmax = __uint_as_float(misc[1]);
+    const float scale = (dmax > dmin) ? (float)nb / (dmax - dmin) : 0.f;
+    // histogram (cur[] = bucket populations)
     for (int i = tid; i < n; i += THREADS) {
-        const unsigned gid = (unsigned)(A[I0[i] & 0xffffu] & 0xffffffffull);
-        ids_sorted[r.x + i] = gid;
+        const float d = __uint_as_float((unsigned)(A[i] >> 32));
+        const int bkt = min(nb - 1, (int)((d - dmin) * scale));               // monotone in d
+        atomicAdd(&cur[bkt], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the nb populations -> start[], cur[] = running cursors.  nb <= 2048 <= 4 per thread at 512 threads.
+    {
+        constexpr int PER = (NBK + THREADS - 1) / THREADS;
+        unsigned v[PER], sum = 0;
+#pragma unroll
+        for (int j = 0; j < PER; j++) { const int b = tid * PER + j; v[j] = (b < nb) ? cur[b] : 0u; sum += v[j]; }
+        unsigned inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) misc[2 + (tid >> 5)] = inc;
+        __syncthreads();
+        unsigned off = 0;
+        for (int w = 0; w < (tid >> 5); w++) off += misc[2 + w];
+        unsigned run = off + inc - sum;
+#pragma unroll
+        for (int j = 0; j < PER; j++) { const int b = tid * PER + j; if (b < nb) { start[b] = run; cur[b] = run; } run += v[j]; }
+        if (tid == 0) start[nb] = (unsigned)n;
+    }
+    __syncthreads();
+    // scatter into buckets (arbitrary order inside a bucket)
+    for (int i = tid; i < n; i += THREADS) {
+        const unsigned long long k = A[i];
+        const float d = __uint_as_float((unsigned)(k >> 32));
+        const int bkt = min(nb - 1, (int)((d - dmin) * scale));
+        B[atomicAdd(&cur[bkt], 1u)] = k;
+    }
+    __syncthreads();
+    // rank inside the bucket with the full key, write id + record to the final position
+    for (int i = tid; i < n; i += THREADS) {
+        const unsigned long long k = B[i];
+        const float d = __uint_as_float((unsigned)(k >> 32));
+        const int bkt = min(nb - 1, (int)((d - dmin) * scale));
+        const int s = (int)start[bkt], e = (int)start[bkt + 1];
+        int rank = 0;
+        for (int j = s; j < e; j++) rank += (B[j] < k) ? 1 : 0;
+        const unsigned gid = (unsigned)(k & 0xffffffffull);
+        const size_t pos = (size_t)r.x + s + rank;
+        ids_sorted[pos] = gid;
         const Rec *src = rec + gid;
         Rec v; v.q0 = __ldg(&src->q0); v.q1 = __ldg(&src->q1); v.q2 = __ldg(&src->q2);
-        rec_sorted[r.x + i] = v;
+        rec_sorted[pos] = v;
     }
     __syncthreads();
 }
 
-constexpr int kSortSmallThreads = 256;
-constexpr int kSortBigThreads = 1024, kSortBigCap = 11264;     // 176 KB keys+items + 16 KB counters
+constexpr int kSortSmallThreads = 512, kSortSmallBuckets = 1024;
+constexpr int kSortBigThreads = 1024, kSortBigCap = 12288, kSortBigBuckets = 2048;     // 192 KB of keys + 16 KB of bucket tables
 
 // grid = tiles: one CTA per tile with 0 < n <= kSortSmallCap
 __global__ void __launch_bounds__(kSortSmallThreads)
@@ -384,7 +349,7 @@ tile_sort_gather_kernel(const unsigned *__restrict__ tile_order, const uint2 *__
     const uint2 r = ranges[tile_order[blockIdx.x]];
     const int n = (int)(r.y - r.x);
     if (n <= 0 || n > kSortSmallCap) return;
-    sort_gather_tile<kSortSmallThreads, kSortSmallCap>(r, keys, rec, ids_sorted, rec_sorted, s_sort);
+    sort_gather_tile<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>(r, keys, rec, ids_sorted, rec_sorted, s_sort);
 }
 
 // small persistent grid walking the list of big tiles
@@ -395,7 +360,7 @@ tile_sort_gather_big_kernel(const TileWork *__restrict__ work, const unsigned *_
     extern __shared__ __align__(16) unsigned char s_sort[];
     const unsigned nb = work->n_big;
     for (unsigned i = blockIdx.x; i < nb; i += gridDim.x)
-        sort_gather_tile<kSortBigThreads, kSortBigCap>(ranges[big_list[i]], keys, rec, ids_sorted, rec_sorted, s_sort);
+        sort_gather_tile<kSortBigThreads, kSortBigCap, kSortBigBuckets>(ranges[big_list[i]], keys, rec, ids_sorted, rec_sorted, s_sort);
 }
 
 }  // namespace dgr

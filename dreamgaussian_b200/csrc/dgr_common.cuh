@@ -35,8 +35,9 @@ static_assert(sizeof(Rec) == 48, "Rec must be 48 bytes");
 constexpr int kGradRecFloats = 12;
 
 struct GeomHeader {
-    unsigned long long n_inst;     // total tile instances of this frame (written by tile_scan_kernel)
-    unsigned int pad[14];
+    unsigned long long n_inst;     // total tile instances of this frame (written by the tile scan)
+    unsigned long long n_big;      // tiles whose population exceeds the per-tile sort CTA (need the big-tile sorter)
+    unsigned int pad[12];
 };
 static_assert(sizeof(GeomHeader) == 64, "GeomHeader");
 
@@ -111,6 +112,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!ok);
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // 1-D bulk TMA: global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).  16-byte aligned, size % 16 == 0.
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {

@@ -140,13 +140,14 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                       const float *__restrict__ scales, const float *__restrict__ rotations,
                       const float *__restrict__ cov3D_precomp,
                       int *__restrict__ radii, Rec *__restrict__ rec, unsigned *__restrict__ touched_out,
-                      unsigned *__restrict__ blk_hist, int tiles, int gpb_iters) {
+                      unsigned *__restrict__ blk_hist, int tiles, int gpb_iters, unsigned *__restrict__ colscan_done) {
     // Per-block tile histogram in shared memory (native integer smem atomics, no global atomics): row `blockIdx.x` of
     // the [blocks x tiles] matrix that tile_colscan_kernel turns into per-(block, tile) offsets.
     extern __shared__ unsigned s_hist[];
     __shared__ FrameConsts fc;
     load_frame(fc, viewmatrix, projmatrix, HAS_SH ? campos : nullptr);
     for (int t = threadIdx.x; t < tiles; t += kPreThreads) s_hist[t] = 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *colscan_done = 0u;      // completion counter of the column-scan kernel
     __syncthreads();
     for (int it = 0; it < gpb_iters; it++) {
     const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + threadIdx.x);

@@ -1,13 +1,15 @@
 // dgr_render.cuh — per-tile front-to-back compositing (A4) and its reverse-traversal backward (A5).
 //
-// B200 design (not the reference's one-thread-per-pixel cooperative fetch):
-//   * a tile's depth-sorted 48-byte records are one contiguous block; one elected thread streams it into shared
-//     memory with 1-D bulk TMA (cp.async.bulk -> UBLKCP) on a 2-stage mbarrier pipeline;
-//   * each warp owns a sub-tile of 32*PPL pixels (PPL = pixels per lane: 8x4, 8x8 or 16x8).  For every batch of 32
-//     staged records each LANE tests ONE record's opacity-aware pixel AABB against the warp's sub-tile, the ballot gives
-//     the records that can touch the sub-tile at all, and only those are evaluated (records are broadcast-read from
-//     shared memory).  This skips most of the (pixel, Gaussian) pairs the reference evaluates and then discards at
-//     alpha < 1/255;
+// B200 design (not the reference's one-thread-per-pixel cooperative fetch with a block barrier per batch):
+//   * a tile's depth-sorted 48-byte records are one contiguous block.  A dedicated PRODUCER warp streams it into a
+//     4-stage shared-memory ring with 1-D bulk TMA (cp.async.bulk -> UBLKCP); "full" mbarriers carry the transaction
+//     bytes, "empty" mbarriers (one arrival per consumer warp) hand a stage back.  There is no block-wide barrier in the
+//     main loop: every consumer warp runs through the tile's list at its own pace (up to 3 chunks ahead of the slowest);
+//   * each consumer warp owns a sub-tile of 32*PPL pixels (PPL = pixels per lane: 8x4, 8x8 or 16x8).  For every batch of
+//     32 staged records each LANE tests ONE record's opacity-aware pixel AABB against the warp's sub-tile, the ballot
+//     gives the records that can touch the sub-tile at all, and only those are evaluated (records are broadcast-read
+//     from shared memory).  This skips most of the (pixel, Gaussian) pairs the reference evaluates and then discards
+//     at alpha < 1/255;
 //   * tiles are issued heaviest-first (tile_order from the scan kernel), so the long tiles do not form the tail;
 //   * backward: per (warp, record) the 10 partial sums are added over the lane's PPL pixels, reduced over the warp with
 //     a 13-shuffle recursive-halving butterfly (warp-shuffle reduction) and land on 10 lanes which issue ONE
@@ -19,7 +21,8 @@
 
 namespace dgr {
 
-constexpr int kChunk = 256;   // records per shared-memory stage (12 KB)
+constexpr int kChunk = 128;   // records per shared-memory stage (6 KB)
+constexpr int kStages = 4;    // bulk-TMA ring depth (24 KB of shared memory per CTA)
 
 // power * log2(e) for pixel offset (dx, dy); identical instruction sequence in forward and backward so both make
 // the same skip decisions.   q0.z = -0.5 A log2e, q0.w = -B log2e, q1.x = -0.5 C log2e
@@ -33,10 +36,11 @@ __device__ __forceinline__ bool aabb_hit(unsigned ax, unsigned ay, int wx0, int 
     return (gx0 <= wx1) & (gx1 >= wx0) & (gy0 <= wy1) & (gy1 >= wy0);
 }
 
-// Sub-tile geometry of one warp for PPL pixels per lane.
+// Sub-tile geometry of one consumer warp for PPL pixels per lane.
 template <int PPL>
 struct SubTile {
-    static constexpr int kThreads = kTileThreads / PPL;
+    static constexpr int kWarps = 8 / PPL;                 // consumer warps per tile
+    static constexpr int kThreads = (kWarps + 1) * 32;     // + the producer warp
     static constexpr int kW = (PPL == 4) ? 16 : 8;         // region width
     static constexpr int kH = (PPL == 1) ? 4 : 8;          // region height
     __device__ static __forceinline__ int x0(int tx, int warp) { return tx * kTile + ((PPL == 4) ? 0 : (warp & 1) * 8); }
@@ -45,18 +49,62 @@ struct SubTile {
     __device__ static __forceinline__ int py(int wy0, int lane, int p) { return wy0 + (lane >> 3) + ((PPL == 4) ? (p >> 1) * 4 : p * 4); }
 };
 
+struct RingSmem {
+    Rec rec[kStages][kChunk];
+    uint64_t full[kStages], empty[kStages];
+    unsigned done_warps;      // forward: consumer warps whose pixels are all finished
+    unsigned maxlast;         // backward: longest per-pixel list of the tile
+};
+
 template <int PPL>
-__global__ void __launch_bounds__(kTileThreads / PPL)
+__global__ void __launch_bounds__(SubTile<PPL>::kThreads)
 render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const uint2 *__restrict__ ranges,
                   const Rec *__restrict__ rec_sorted, const float *__restrict__ bg, float *__restrict__ out_color,
                   float *__restrict__ out_depth, float *__restrict__ out_alpha, unsigned *__restrict__ n_contrib,
                   float *__restrict__ final_T) {
     using ST = SubTile<PPL>;
-    __shared__ __align__(128) Rec s_rec[2][kChunk];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    constexpr unsigned NW = ST::kWarps;
+    __shared__ __align__(128) RingSmem sm;
     const int tile = tile_order ? (int)tile_order[blockIdx.x] : (int)blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint2 range = ranges[tile];
+    const int n = (int)(range.y - range.x);
+    const int nchunks = (n + kChunk - 1) / kChunk;
+    const Rec *src = rec_sorted + range.x;
+    volatile unsigned *vdone = &sm.done_warps;
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kStages; i++) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], NW); }
+        sm.done_warps = 0;
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == (int)NW) {
+        // ------------------------------- producer warp: one elected lane drives the TMA ring -------------------------------
+        if (lane == 0) {
+            int issued = 0;
+            for (int c = 0; c < nchunks; c++) {
+                const int st = c % kStages;
+                bool stop = false;
+                if (c >= kStages) {            // wait until every consumer warp released chunk c - kStages
+                    const uint32_t par = (uint32_t)(((c / kStages) - 1) & 1);
+                    while (!mbar_try_wait(&sm.empty[st], par)) { if (*vdone == NW) { stop = true; break; } }
+                }
+                if (stop || *vdone == NW) break;
+                const uint32_t bytes = (uint32_t)min(kChunk, n - c * kChunk) * (uint32_t)sizeof(Rec);
+                mbar_expect_tx(&sm.full[st], bytes);
+                tma_bulk_g2s(&sm.rec[st][0], src + (size_t)c * kChunk, bytes, &sm.full[st]);
+                issued = c + 1;
+            }
+            // never leave the CTA with a bulk copy in flight into its shared memory
+            for (int cc = max(0, issued - kStages); cc < issued; cc++) mbar_wait(&sm.full[cc % kStages], (uint32_t)((cc / kStages) & 1));
+        }
+        return;
+    }
+
+    // ------------------------------------------------- consumer warps -------------------------------------------------
     const int wx0 = ST::x0(tx, warp), wy0 = ST::y0(ty, warp);
     const int wx1 = wx0 + ST::kW - 1, wy1 = wy0 + ST::kH - 1;
     float fx[PPL], fy[PPL], T[PPL], C0[PPL], C1[PPL], C2[PPL], D[PPL];
@@ -71,41 +119,22 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
         T[p] = 1.f; C0[p] = 0.f; C1[p] = 0.f; C2[p] = 0.f; D[p] = 0.f; last[p] = 0; done[p] = !inside[p];
         all_done = all_done && done[p];
     }
-    const uint2 range = ranges[tile];
-    const int n = (int)(range.y - range.x);
-    const int nchunks = (n + kChunk - 1) / kChunk;
-    const Rec *src = rec_sorted + range.x;
-
-    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
-    __syncthreads();
-    if (tid == 0 && nchunks > 0) {
-        const uint32_t bytes = (uint32_t)min(kChunk, n) * (uint32_t)sizeof(Rec);
-        mbar_expect_tx(&s_bar[0], bytes);
-        tma_bulk_g2s(&s_rec[0][0], src, bytes, &s_bar[0]);
-    }
-    bool warp_done = false;
-    int c = 0;
-    bool pending_next = false;
-    for (; c < nchunks; c++) {
-        const int s = c & 1;
-        if (tid == 0 && c + 1 < nchunks) {
-            const uint32_t bytes = (uint32_t)min(kChunk, n - (c + 1) * kChunk) * (uint32_t)sizeof(Rec);
-            mbar_expect_tx(&s_bar[s ^ 1], bytes);
-            tma_bulk_g2s(&s_rec[s ^ 1][0], src + (size_t)(c + 1) * kChunk, bytes, &s_bar[s ^ 1]);
-        }
-        pending_next = (c + 1 < nchunks);
-        mbar_wait(&s_bar[s], (uint32_t)((c >> 1) & 1));
-        const int cnt = min(kChunk, n - c * kChunk);
+    bool warp_done = __all_sync(0xffffffffu, all_done);
+    if (warp_done && lane == 0) atomicAdd(&sm.done_warps, 1u);
+    for (int c = 0; c < nchunks; c++) {
+        const int s = c % kStages;
         if (!warp_done) {
+            mbar_wait(&sm.full[s], (uint32_t)((c / kStages) & 1));
+            const int cnt = min(kChunk, n - c * kChunk);
             for (int b = 0; b < cnt; b += 32) {
                 const int i = b + lane;
                 bool hit = false;
-                if (i < cnt) hit = aabb_hit(__float_as_uint(s_rec[s][i].q1.w), __float_as_uint(s_rec[s][i].q2.w), wx0, wx1, wy0, wy1);
+                if (i < cnt) hit = aabb_hit(__float_as_uint(sm.rec[s][i].q1.w), __float_as_uint(sm.rec[s][i].q2.w), wx0, wx1, wy0, wy1);
                 unsigned mask = __ballot_sync(0xffffffffu, hit);
                 while (mask) {
                     const int j = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const Rec *r = &s_rec[s][b + j];
+                    const Rec *r = &sm.rec[s][b + j];
                     const float4 q0 = r->q0, q1 = r->q1;
                     float4 q2;
                     bool have_q2 = false;
@@ -133,12 +162,24 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
                 for (int p = 0; p < PPL; p++) all_done = all_done && done[p];
                 if (__all_sync(0xffffffffu, all_done)) { warp_done = true; break; }
             }
+            __syncwarp();
+            if (lane == 0) {
+                if (warp_done) atomicAdd(&sm.done_warps, 1u);
+                mbar_arrive(&sm.empty[s]);
+            }
+        } else {
+            // finished warp: keep handing stages back (in phase order) until every warp of the tile is finished
+            if (*vdone == NW) break;
+            bool stop = false;
+            if (c >= kStages) {
+                const uint32_t par = (uint32_t)(((c / kStages) - 1) & 1);
+                while (!mbar_try_wait(&sm.empty[s], par)) { if (*vdone == NW) { stop = true; break; } }
+            }
+            if (stop) break;
+            if (lane == 0) mbar_arrive(&sm.empty[s]);
+            __syncwarp();
         }
-        const int ndone = __syncthreads_count(all_done ? 1 : 0);
-        if (ndone == ST::kThreads) { c++; break; }
     }
-    // never leave the CTA with a bulk copy still in flight into its shared memory
-    if (pending_next && c < nchunks && tid == 0) mbar_wait(&s_bar[c & 1], (uint32_t)((c >> 1) & 1));
 
     const float b0 = __ldg(bg), b1 = __ldg(bg + 1), b2 = __ldg(bg + 2);
     const size_t HW = (size_t)H * W;
@@ -183,23 +224,23 @@ __device__ __forceinline__ float reduce12(const float (&v)[12], int lane) {
 }
 
 template <int PPL>
-__global__ void __launch_bounds__(kTileThreads / PPL)
+__global__ void __launch_bounds__(SubTile<PPL>::kThreads)
 render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const uint2 *__restrict__ ranges,
                   const Rec *__restrict__ rec_sorted, const unsigned *__restrict__ ids_sorted, const float *__restrict__ bg,
                   const float *__restrict__ final_T, const unsigned *__restrict__ n_contrib,
                   const float *__restrict__ gC, const float *__restrict__ gD, const float *__restrict__ gA,
                   float *__restrict__ grad_rec) {
     using ST = SubTile<PPL>;
-    __shared__ __align__(128) Rec s_rec[2][kChunk];
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ unsigned s_maxlast;
+    constexpr unsigned NW = ST::kWarps;
+    __shared__ __align__(128) RingSmem sm;
     const int tile = tile_order ? (int)tile_order[blockIdx.x] : (int)blockIdx.x;
     const int tx = tile % gx, ty = tile / gx;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wx0 = ST::x0(tx, warp), wy0 = ST::y0(ty, warp);
-    const int wx1 = wx0 + ST::kW - 1, wy1 = wy0 + ST::kH - 1;
     const uint2 range = ranges[tile];
     if (range.y == range.x) return;
+    const bool producer = warp == (int)NW;
+    const int wx0 = ST::x0(tx, producer ? 0 : warp), wy0 = ST::y0(ty, producer ? 0 : warp);
+    const int wx1 = wx0 + ST::kW - 1, wy1 = wy0 + ST::kH - 1;
 
     float fx[PPL], fy[PPL], gc0[PPL], gc1[PPL], gc2[PPL], gd[PPL], ga[PPL], T[PPL], R[PPL];
     unsigned last[PPL];
@@ -211,7 +252,7 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
         const int x = ST::px(wx0, lane, p), y = ST::py(wy0, lane, p);
         fx[p] = (float)x; fy[p] = (float)y;
         gc0[p] = 0.f; gc1[p] = 0.f; gc2[p] = 0.f; gd[p] = 0.f; ga[p] = 0.f; T[p] = 1.f; last[p] = 0;
-        if ((x < W) && (y < H)) {
+        if (!producer && (x < W) && (y < H)) {
             const size_t pix = (size_t)y * W + x;
             last[p] = n_contrib[pix];
             T[p] = __ldg(final_T + pix);
@@ -223,97 +264,112 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
         R[p] = T[p] * (b0 * gc0[p] + b1 * gc1[p] + b2 * gc2[p]);
         lmax = max(lmax, last[p]);
     }
-
-    if (tid == 0) { s_maxlast = 0; mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kStages; i++) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], NW); }
+        sm.maxlast = 0;
+        mbar_fence_init();
+    }
     __syncthreads();
     unsigned wmax = lmax;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane == 0 && wmax) atomicMax(&s_maxlast, wmax);
+    if (lane == 0 && wmax) atomicMax(&sm.maxlast, wmax);
     __syncthreads();
-    const int n = (int)s_maxlast;                       // records [0, n) of this tile's list matter
+    const int n = (int)sm.maxlast;                      // records [0, n) of this tile's list matter
     const int nchunks = (n + kChunk - 1) / kChunk;
     const Rec *src = rec_sorted + range.x;
     const unsigned *ids = ids_sorted + range.x;
     const unsigned wlast = wmax;                        // warp-level bound
 
-    if (tid == 0 && nchunks > 0) {
-        const int c0 = nchunks - 1;
-        const uint32_t bytes = (uint32_t)(n - c0 * kChunk) * (uint32_t)sizeof(Rec);
-        mbar_expect_tx(&s_bar[0], bytes);
-        tma_bulk_g2s(&s_rec[0][0], src + (size_t)c0 * kChunk, bytes, &s_bar[0]);
+    // step k (0 .. nchunks-1) handles chunk c = nchunks-1-k (back to front) in stage k % kStages
+    if (producer) {
+        if (lane == 0) {
+            for (int k = 0; k < nchunks; k++) {
+                const int c = nchunks - 1 - k, st = k % kStages;
+                if (k >= kStages) mbar_wait(&sm.empty[st], (uint32_t)(((k / kStages) - 1) & 1));
+                const uint32_t bytes = (uint32_t)min(kChunk, n - c * kChunk) * (uint32_t)sizeof(Rec);
+                mbar_expect_tx(&sm.full[st], bytes);
+                tma_bulk_g2s(&sm.rec[st][0], src + (size_t)c * kChunk, bytes, &sm.full[st]);
+            }
+            // every chunk is consumed by the warp that owns the longest list, so all copies have landed before that warp
+            // (and therefore the CTA) can finish; still, wait for the tail explicitly
+            for (int k = max(0, nchunks - kStages); k < nchunks; k++) mbar_wait(&sm.full[k % kStages], (uint32_t)((k / kStages) & 1));
+        }
+        return;
     }
     for (int k = 0; k < nchunks; k++) {
-        const int c = nchunks - 1 - k, s = k & 1;
-        if (tid == 0 && k + 1 < nchunks) {
-            const uint32_t bytes = (uint32_t)kChunk * (uint32_t)sizeof(Rec);   // every chunk but the last is full
-            mbar_expect_tx(&s_bar[s ^ 1], bytes);
-            tma_bulk_g2s(&s_rec[s ^ 1][0], src + (size_t)(c - 1) * kChunk, bytes, &s_bar[s ^ 1]);
+        const int c = nchunks - 1 - k, s = k % kStages;
+        if ((unsigned)(c * kChunk) >= wlast) {
+            // nothing of this chunk reaches this warp's pixels: hand the stage back without touching the data
+            if (k >= kStages) mbar_wait(&sm.empty[s], (uint32_t)(((k / kStages) - 1) & 1));
+            if (lane == 0) mbar_arrive(&sm.empty[s]);
+            __syncwarp();
+            continue;
         }
-        mbar_wait(&s_bar[s], (uint32_t)((k >> 1) & 1));
+        mbar_wait(&sm.full[s], (uint32_t)((k / kStages) & 1));
         const int cnt = min(kChunk, n - c * kChunk);
-        if ((unsigned)(c * kChunk) < wlast) {
-            for (int b = ((cnt - 1) >> 5) << 5; b >= 0; b -= 32) {
-                if ((unsigned)(c * kChunk + b) >= wlast) continue;
-                const int i = b + lane;
-                bool hit = false;
-                unsigned my_id = 0;
-                if (i < cnt) {
-                    hit = aabb_hit(__float_as_uint(s_rec[s][i].q1.w), __float_as_uint(s_rec[s][i].q2.w), wx0, wx1, wy0, wy1);
-                    my_id = __ldg(ids + (size_t)c * kChunk + i);
+        for (int b = ((cnt - 1) >> 5) << 5; b >= 0; b -= 32) {
+            if ((unsigned)(c * kChunk + b) >= wlast) continue;
+            const int i = b + lane;
+            bool hit = false;
+            unsigned my_id = 0;
+            if (i < cnt) {
+                hit = aabb_hit(__float_as_uint(sm.rec[s][i].q1.w), __float_as_uint(sm.rec[s][i].q2.w), wx0, wx1, wy0, wy1);
+                my_id = __ldg(ids + (size_t)c * kChunk + i);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, hit);
+            while (mask) {
+                const int j = 31 - __clz(mask);
+                mask &= ~(1u << j);
+                const Rec *r = &sm.rec[s][b + j];
+                const float4 q0 = r->q0, q1 = r->q1;
+                const unsigned gidx = (unsigned)(c * kChunk + b + j);
+                float dxv[PPL], dyv[PPL], agv[PPL], av[PPL];
+                bool okv[PPL];
+                bool any_ok = false;
+#pragma unroll
+                for (int p = 0; p < PPL; p++) {
+                    dxv[p] = q0.x - fx[p]; dyv[p] = q0.y - fy[p];
+                    const float p2 = eval_power2(q0, q1, dxv[p], dyv[p]);
+                    agv[p] = __fmul_rn(q1.y, ex2_approx(p2));
+                    av[p] = fminf(DGR_ALPHA_MAX, agv[p]);
+                    okv[p] = (gidx < last[p]) & (p2 <= 0.f) & (av[p] >= DGR_ALPHA_MIN);
+                    any_ok = any_ok || okv[p];
                 }
-                unsigned mask = __ballot_sync(0xffffffffu, hit);
-                while (mask) {
-                    const int j = 31 - __clz(mask);
-                    mask &= ~(1u << j);
-                    const Rec *r = &s_rec[s][b + j];
-                    const float4 q0 = r->q0, q1 = r->q1;
-                    const unsigned gidx = (unsigned)(c * kChunk + b + j);
-                    float dxv[PPL], dyv[PPL], agv[PPL], av[PPL];
-                    bool okv[PPL];
-                    bool any_ok = false;
+                if (!__any_sync(0xffffffffu, any_ok)) continue;
+                float v[12];
+#pragma unroll
+                for (int q = 0; q < 12; q++) v[q] = 0.f;
+                if (any_ok) {
+                    const float4 q2 = r->q2;
 #pragma unroll
                     for (int p = 0; p < PPL; p++) {
-                        dxv[p] = q0.x - fx[p]; dyv[p] = q0.y - fy[p];
-                        const float p2 = eval_power2(q0, q1, dxv[p], dyv[p]);
-                        agv[p] = __fmul_rn(q1.y, ex2_approx(p2));
-                        av[p] = fminf(DGR_ALPHA_MAX, agv[p]);
-                        okv[p] = (gidx < last[p]) & (p2 <= 0.f) & (av[p] >= DGR_ALPHA_MIN);
-                        any_ok = any_ok || okv[p];
-                    }
-                    if (!__any_sync(0xffffffffu, any_ok)) continue;
-                    float v[12];
-#pragma unroll
-                    for (int q = 0; q < 12; q++) v[q] = 0.f;
-                    if (any_ok) {
-                        const float4 q2 = r->q2;
-#pragma unroll
-                        for (int p = 0; p < PPL; p++) {
-                            if (okv[p]) {
-                                const float ir = rcp_approx(1.f - av[p]);
-                                T[p] = T[p] * ir;
-                                const float sdot = __fmaf_rn(q2.x, gc0[p], __fmaf_rn(q2.y, gc1[p], __fmaf_rn(q2.z, gc2[p], __fmaf_rn(q1.z, gd[p], ga[p]))));
-                                const float dL_da = T[p] * sdot - R[p] * ir;
-                                const float w = av[p] * T[p];
-                                R[p] = __fmaf_rn(w, sdot, R[p]);
-                                const float u = agv[p] * dL_da;
-                                const float udx = u * dxv[p], udy = u * dyv[p];
-                                v[0] += u; v[1] += udx; v[2] += udy;
-                                v[3] = __fmaf_rn(udx, dxv[p], v[3]); v[4] = __fmaf_rn(udx, dyv[p], v[4]); v[5] = __fmaf_rn(udy, dyv[p], v[5]);
-                                v[6] = __fmaf_rn(w, gc0[p], v[6]); v[7] = __fmaf_rn(w, gc1[p], v[7]); v[8] = __fmaf_rn(w, gc2[p], v[8]);
-                                v[9] = __fmaf_rn(w, gd[p], v[9]);
-                            }
+                        if (okv[p]) {
+                            const float ir = rcp_approx(1.f - av[p]);
+                            T[p] = T[p] * ir;
+                            const float sdot = __fmaf_rn(q2.x, gc0[p], __fmaf_rn(q2.y, gc1[p], __fmaf_rn(q2.z, gc2[p], __fmaf_rn(q1.z, gd[p], ga[p]))));
+                            const float dL_da = T[p] * sdot - R[p] * ir;
+                            const float w = av[p] * T[p];
+                            R[p] = __fmaf_rn(w, sdot, R[p]);
+                            const float u = agv[p] * dL_da;
+                            const float udx = u * dxv[p], udy = u * dyv[p];
+                            v[0] += u; v[1] += udx; v[2] += udy;
+                            v[3] = __fmaf_rn(udx, dxv[p], v[3]); v[4] = __fmaf_rn(udx, dyv[p], v[4]); v[5] = __fmaf_rn(udy, dyv[p], v[5]);
+                            v[6] = __fmaf_rn(w, gc0[p], v[6]); v[7] = __fmaf_rn(w, gc1[p], v[7]); v[8] = __fmaf_rn(w, gc2[p], v[8]);
+                            v[9] = __fmaf_rn(w, gd[p], v[9]);
                         }
                     }
-                    const float red = reduce12(v, lane);
-                    const unsigned gid = __shfl_sync(0xffffffffu, my_id, j);
-                    const int comp = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0) + ((lane >> 1) & 3);
-                    if (((lane & 1) == 0) && ((lane & 6) != 6) && comp < 10)
-                        red_add_f32(grad_rec + (size_t)gid * kGradRecFloats + comp, red);
                 }
+                const float red = reduce12(v, lane);
+                const unsigned gid = __shfl_sync(0xffffffffu, my_id, j);
+                const int comp = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0) + ((lane >> 1) & 3);
+                if (((lane & 1) == 0) && ((lane & 6) != 6) && comp < 10)
+                    red_add_f32(grad_rec + (size_t)gid * kGradRecFloats + comp, red);
             }
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);
     }
 }
 

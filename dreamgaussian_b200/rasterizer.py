@@ -124,20 +124,19 @@ def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, 
                                               _ptr(radii), st))
         out = _lib.DgrImages(_ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii))
         key = (dev.index, P, H, W)
-        cap = _CAPACITY_HINT.get(key)
-        if cap is None:
-            cap = max(65536, 16 * P)
+        cap, big = _CAPACITY_HINT.get(key, (max(65536, 16 * P), True))
         while True:
             binning = torch.empty((lib.dgr_binning_bytes(cap, H, W),), **u8)
             _lib.check(lib.dgr_forward_render(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(binning),
-                                              ctypes.c_uint64(cap), _ptr(image), ctypes.byref(out),
+                                              ctypes.c_uint64(cap), _ptr(image), ctypes.byref(out), 1 if big else 0,
                                               ctypes.c_void_p(n_host.data_ptr()), event, st))
             _lib.check(lib.dgr_event_synchronize(event))
-            n_inst = int(n_host[0])
-            if n_inst <= cap:
+            n_inst, n_big = int(n_host[0]), int(n_host[1])
+            if n_inst <= cap and (big or n_big == 0):
                 break
-            cap = int(n_inst * 1.25) + 4096            # the guess was too small: redo stage 2 (rare)
-        _CAPACITY_HINT[key] = max(int(n_inst * 1.25) + 4096, 65536)
+            cap = max(cap, int(n_inst * 1.25) + 4096)  # a guess was wrong: redo stage 2 (rare)
+            big = big or n_big > 0
+        _CAPACITY_HINT[key] = (max(int(n_inst * 1.25) + 4096, 65536), n_big > 0)
     state = ForwardState()
     state.rs, state.frame, state.num_rendered, state.capacity = rs, fr, n_inst, cap
     state.geom, state.binning, state.image, state.radii, state.alpha = geom, binning, image, radii, alpha
@@ -158,7 +157,7 @@ def _host_sync_objects(dev):
         ev = _lib.load().dgr_event_create()
         if not ev:
             raise RuntimeError("libdgr_b200: could not create a CUDA event")
-        t = (torch.zeros((1,), dtype=torch.int64).pin_memory(), ctypes.c_void_p(ev))
+        t = (torch.zeros((2,), dtype=torch.int64).pin_memory(), ctypes.c_void_p(ev))
         _SYNC[key] = t
     return t
 

@@ -92,16 +92,19 @@ size_t dgr_binning_bytes(uint64_t capacity_instances, int32_t image_height, int3
 int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *geom, void *image, int32_t *radii,
                            void *stream);
 
-/* Forward, stage 2: tile ranges (device-side scan), instance emission, per-tile depth sort + record gather, and the
- * per-tile front-to-back compositing.  Nothing here waits for the host: `capacity_instances` is the instance capacity
- * `binning` was sized for (a guess is fine).  The true instance count is written to geom scratch and, if
- * n_instances_host != NULL (pinned host memory), copied there asynchronously right after the scan; if
- * count_ready_event != NULL (from dgr_event_create) it is recorded at that point, so the caller can keep enqueuing
- * work and check `*n_instances_host <= capacity_instances` once that event has fired.  If the count exceeds the
- * capacity the call rendered a truncated (but memory-safe) instance list: re-run stage 2 with a larger buffer. */
+/* Forward, stage 2: tile ranges (device-side scans), instance emission, per-tile depth sort + record gather, and the
+ * per-tile front-to-back compositing.  Nothing here waits for the host.  Two things are guessed by the caller:
+ *   - `capacity_instances`, the instance capacity `binning` was sized for;
+ *   - DGR_FLAG_BIG_TILES in `flags`: whether to also launch the sorter for tiles with more than 4096 instances.
+ * The truth is written to geom scratch and, if counts_host != NULL (pinned host memory, 2 x uint64), copied there
+ * asynchronously right after the scan: counts_host[0] = instance count, counts_host[1] = number of big tiles; if
+ * count_ready_event != NULL (from dgr_event_create) it is recorded at that point, so the caller keeps enqueuing work and
+ * checks the guesses once that event has fired.  If counts_host[0] > capacity_instances, or counts_host[1] > 0 without
+ * DGR_FLAG_BIG_TILES, the call produced a memory-safe but wrong image: re-run stage 2 with corrected guesses. */
+#define DGR_FLAG_BIG_TILES 1
 int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom, void *binning,
-                       uint64_t capacity_instances, void *image, const DgrImages *out,
-                       uint64_t *n_instances_host, void *count_ready_event, void *stream);
+                       uint64_t capacity_instances, void *image, const DgrImages *out, int32_t flags,
+                       uint64_t *counts_host, void *count_ready_event, void *stream);
 
 /* Tuning knobs (process-wide; results do not depend on them): pixels per lane of the forward / backward render
  * kernels (1, 2 or 4) and whether tiles are issued heaviest-first (1) or in row-major order (0). */

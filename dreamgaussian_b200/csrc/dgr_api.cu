@@ -72,6 +72,7 @@ int check_settings(const DgrSettings *s) {
 int check_gaussians(const DgrSettings *s, const DgrGaussians *g) {
     if (!g) return fail(-1, "gaussians is NULL");
     if (g->P < 0) return fail(-1, "P < 0");
+    if (g->P == 0) return 0;                       // empty cloud: empty tensors have NULL data pointers
     if ((g->shs == nullptr) == (g->colors_precomp == nullptr))
         return fail(-2, "Please provide excatly one of either SHs or precomputed colors!");
     if (((g->scales == nullptr || g->rotations == nullptr) && g->cov3D_precomp == nullptr) ||

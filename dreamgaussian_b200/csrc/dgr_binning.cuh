@@ -204,16 +204,11 @@ emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, const Rec *__rest
         if (g >= P) continue;
         if (touched[g] == 0) continue;
         const float4 q1 = rec[g].q1;
-        const unsigned ax = __float_as_uint(q1.w), ay = __float_as_uint(rec[g].q2.w);
-        const int tx0 = (int)(ax & 0xffffu) >> 4, tx1 = (int)(ax >> 16) >> 4;
-        const int ty0 = (int)(ay & 0xffffu) >> 4, ty1 = (int)(ay >> 16) >> 4;
         const unsigned long long key = ((unsigned long long)__float_as_uint(q1.z) << 32) | (unsigned)g;
-        for (int y = ty0; y <= ty1; y++)
-            for (int x = tx0; x <= tx1; x++) {
-                const int t = y * gx + x;
-                const unsigned pos = atomicAdd(&s_off[t], 1u);
-                if (pos < __ldg(&ranges[t].y)) keys[pos] = key;           // beyond the (clipped) range: dropped
-            }
+        for_each_touched_tile(__float_as_uint(q1.w), __float_as_uint(rec[g].q2.w), gx, [&](int t) {
+            const unsigned pos = atomicAdd(&s_off[t], 1u);
+            if (pos < __ldg(&ranges[t].y)) keys[pos] = key;               // beyond the (clipped) range: dropped
+        });
     }
 }
 

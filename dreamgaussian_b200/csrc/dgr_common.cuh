@@ -137,5 +137,46 @@ __device__ __forceinline__ void red_add_f32(float *addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ float4 ldg_f4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+
+// power*log2(e) below which a Gaussian of opacity o cannot reach alpha = 1/255 (minus a safety margin of 1% in alpha)
+__device__ __forceinline__ float alpha_threshold_power2(float opacity) { return -7.9943534f - lg2_approx(opacity) - 0.015f; }
+
+// Conservative exact test: can ANY point of the pixel rectangle [x0,x1] x [y0,y1] reach power2 >= thr2 for the Gaussian
+// with centre (cx, cy) and power2(dx, dy) = nA dx^2 + nB dx dy + nC dy^2 (nA, nC < 0, negative definite)?
+// The maximiser of a concave quadratic over a box is the centre if it lies inside, otherwise it lies on one of the (at most
+// two) edges facing the centre, where it is the clamped 1-D maximiser.
+__device__ __forceinline__ bool ellipse_hits_rect(float cx, float cy, float nA, float nB, float nC, float thr2,
+                                                  float x0, float x1, float y0, float y1) {
+    const float xe = fminf(fmaxf(cx, x0), x1), ye = fminf(fmaxf(cy, y0), y1);
+    const float dxe = cx - xe, dye = cy - ye;
+    if (dxe == 0.f && dye == 0.f) return true;
+    float best = -3.0e38f;
+    if (dxe != 0.f) {
+        float dy = -0.5f * nB * dxe * rcp_approx(nC);
+        dy = fminf(fmaxf(dy, cy - y1), cy - y0);
+        best = nA * dxe * dxe + nB * dxe * dy + nC * dy * dy;
+    }
+    if (dye != 0.f) {
+        float dx = -0.5f * nB * dye * rcp_approx(nA);
+        dx = fminf(fmaxf(dx, cx - x1), cx - x0);
+        best = fmaxf(best, nA * dx * dx + nB * dx * dye + nC * dye * dye);
+    }
+    return best >= thr2;
+}
+
+// The tiles a Gaussian is binned into: those of its opacity-aware pixel AABB (which already carries the reference's
+// 3-sigma tile-rect clip).  Used — with the SAME packed record values — by the preprocess histogram and by the emit kernel,
+// so both make identical decisions.  (The exact ellipse test is applied later, per warp sub-tile, in the render kernels:
+// measured on B200 it costs more in these two latency-bound per-Gaussian loops than the ~8% of instances it removes.)
+template <class F>
+__device__ __forceinline__ void for_each_touched_tile(unsigned ax, unsigned ay, int gx, F f) {
+    const int bx0 = (int)(ax & 0xffffu), bx1 = (int)(ax >> 16), by0 = (int)(ay & 0xffffu), by1 = (int)(ay >> 16);
+    if (bx0 > bx1 || by0 > by1) return;
+    for (int ty = by0 >> 4; ty <= (by1 >> 4); ty++)
+        for (int tx = bx0 >> 4; tx <= (bx1 >> 4); tx++) f(ty * gx + tx);
+}
 
 }  // namespace dgr

@@ -221,16 +221,14 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                         bx1 = min(min(rmaxx * kTile, W) - 1, (int)floorf(fminf(mx + ex, lim)));
                         by1 = min(min(rmaxy * kTile, H) - 1, (int)floorf(fminf(my + ey, lim)));
                     }
-                    if (bx0 <= bx1 && by0 <= by1) {
-                        touched = (unsigned)(((bx1 >> 4) - (bx0 >> 4) + 1) * ((by1 >> 4) - (by0 >> 4) + 1));
-                        // per-tile instance histogram (tile_scan_kernel turns it into ranges)
-                        for (int ty = by0 >> 4; ty <= (by1 >> 4); ty++)
-                            for (int tx = bx0 >> 4; tx <= (bx1 >> 4); tx++) atomicAdd(&s_hist[ty * gx + tx], 1u);
-                    } else { bx0 = 1; bx1 = 0; by0 = 1; by1 = 0; }
+                    if (!(bx0 <= bx1 && by0 <= by1)) { bx0 = 1; bx1 = 0; by0 = 1; by1 = 0; }
                     // conic stored as the coefficients of power*log2(e): -0.5 A log2e, -B log2e, -0.5 C log2e
                     r.q0 = make_float4(mx, my, cA * (-0.5f * kLog2e), cB * (-kLog2e));
                     r.q1 = make_float4(cC * (-0.5f * kLog2e), o, geo.t[2], __uint_as_float((unsigned)bx0 | ((unsigned)bx1 << 16)));
                     r.q2 = make_float4(cr, cg, cb, __uint_as_float((unsigned)by0 | ((unsigned)by1 << 16)));
+                    // per-tile instance histogram of this block (tile_colscan_kernel turns the rows into offsets)
+                    for_each_touched_tile(__float_as_uint(r.q1.w), __float_as_uint(r.q2.w), gx,
+                                          [&](int t) { atomicAdd(&s_hist[t], 1u); touched++; });
                 }
             }
         }

@@ -36,6 +36,18 @@ __device__ __forceinline__ bool aabb_hit(unsigned ax, unsigned ay, int wx0, int 
     return (gx0 <= wx1) & (gx1 >= wx0) & (gy0 <= wy1) & (gy1 >= wy0);
 }
 
+// Lane-level cull of one staged record against a warp's sub-tile [wx0,wx1] x [wy0,wy1]: the opacity-aware pixel AABB
+// (which carries the reference's 3-sigma tile-rect clip) AND the exact "can the alpha >= 1/255 ellipse reach it" test.
+__device__ __forceinline__ bool record_hits_subtile(const Rec &r, int wx0, int wx1, int wy0, int wy1) {
+    const float4 q1 = r.q1;
+    const unsigned ax = __float_as_uint(q1.w), ay = __float_as_uint(r.q2.w);
+    const int gx0 = (int)(ax & 0xffffu), gx1 = (int)(ax >> 16), gy0 = (int)(ay & 0xffffu), gy1 = (int)(ay >> 16);
+    const int x0 = max(gx0, wx0), x1 = min(gx1, wx1), y0 = max(gy0, wy0), y1 = min(gy1, wy1);
+    if (x0 > x1 || y0 > y1) return false;
+    const float4 q0 = r.q0;
+    return ellipse_hits_rect(q0.x, q0.y, q0.z, q0.w, q1.x, alpha_threshold_power2(q1.y), (float)x0, (float)x1, (float)y0, (float)y1);
+}
+
 // Sub-tile geometry of one consumer warp for PPL pixels per lane.
 template <int PPL>
 struct SubTile {
@@ -129,7 +141,7 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
             for (int b = 0; b < cnt; b += 32) {
                 const int i = b + lane;
                 bool hit = false;
-                if (i < cnt) hit = aabb_hit(__float_as_uint(sm.rec[s][i].q1.w), __float_as_uint(sm.rec[s][i].q2.w), wx0, wx1, wy0, wy1);
+                if (i < cnt) hit = record_hits_subtile(sm.rec[s][i], wx0, wx1, wy0, wy1);
                 unsigned mask = __ballot_sync(0xffffffffu, hit);
                 while (mask) {
                     const int j = __ffs(mask) - 1;
@@ -315,7 +327,7 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
             bool hit = false;
             unsigned my_id = 0;
             if (i < cnt) {
-                hit = aabb_hit(__float_as_uint(sm.rec[s][i].q1.w), __float_as_uint(sm.rec[s][i].q2.w), wx0, wx1, wy0, wy1);
+                hit = record_hits_subtile(sm.rec[s][i], wx0, wx1, wy0, wy1);
                 my_id = __ldg(ids + (size_t)c * kChunk + i);
             }
             unsigned mask = __ballot_sync(0xffffffffu, hit);

@@ -104,12 +104,12 @@ void launch_pre_fwd(const DgrSettings *s, const DgrGaussians *g, int *radii, cha
 }
 
 template <int DEG, bool HAS_SH, bool HAS_COV>
-void launch_pre_bwd(const DgrSettings *s, const DgrGaussians *g, const int *radii, const float *grad_rec,
+void launch_pre_bwd(const DgrSettings *s, const DgrGaussians *g, const int *radii, const unsigned *touched, const float *grad_rec,
                     const DgrGaussianGrads *o, cudaStream_t st) {
     const int nb = (g->P + kPreThreads - 1) / kPreThreads;
     preprocess_bwd_kernel<DEG, HAS_SH, HAS_COV><<<nb, kPreThreads, 0, st>>>(
         g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
-        s->campos, g->means3D, g->shs, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii, grad_rec,
+        s->campos, g->means3D, g->shs, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii, touched, grad_rec,
         o->dL_dmeans3D, o->dL_dmeans2D, o->dL_dshs, o->dL_dcolors_precomp, o->dL_dopacities, o->dL_dscales, o->dL_drotations,
         o->dL_dcov3D_precomp, o->accumulate);
 }
@@ -139,7 +139,7 @@ __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched
         const unsigned ax = __float_as_uint(r.q1.w), ay = __float_as_uint(r.q2.w);
         aabb[4 * g] = (int)(ax & 0xffffu); aabb[4 * g + 1] = (int)(ay & 0xffffu); aabb[4 * g + 2] = (int)(ax >> 16); aabb[4 * g + 3] = (int)(ay >> 16);
     }
-    if (tiles_touched) tiles_touched[g] = touched[g];
+    if (tiles_touched) tiles_touched[g] = touched[g] & 0x1fffffffu;
 }
 
 bool g_sort_attr_set = false;
@@ -247,9 +247,13 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
     unsigned *tile_order = reinterpret_cast<unsigned *>(image + IL.off_order);
     unsigned *big_list = reinterpret_cast<unsigned *>(image + IL.off_biglist);
     TileWork *work = reinterpret_cast<TileWork *>(image + IL.off_work);
-    DGR_KERNEL("tile_colscan_scan", st, s->debug,
-               tile_colscan_kernel<<<(tiles + 31) / 32, 1024, 0, st>>>(tiles, GL.nblocks, blk_hist, tile_count, (unsigned long long)capacity,
-                                                                        ranges, hdr, tile_order, work, big_list));
+    if (flags & DGR_FLAG_RERUN)
+        DGR_KERNEL("tile_scan", st, s->debug,
+                   tile_scan_kernel<<<1, 1024, 0, st>>>(tiles, tile_count, (unsigned long long)capacity, ranges, hdr, tile_order, work, big_list));
+    else
+        DGR_KERNEL("tile_colscan_scan", st, s->debug,
+                   tile_colscan_kernel<<<(tiles + 31) / 32, 1024, 0, st>>>(tiles, GL.nblocks, blk_hist, tile_count, (unsigned long long)capacity,
+                                                                            ranges, hdr, tile_order, work, big_list));
     if (counts_host)      // { n_instances, n_big_tiles }
         DGR_CUDA(cudaMemcpyAsync(counts_host, geom, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     if (count_ready_event) DGR_CUDA(cudaEventRecord((cudaEvent_t)count_ready_event, st));
@@ -316,7 +320,7 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
         if (g_ppl_bwd == 4) DGR_RENDER_BWD(4); else if (g_ppl_bwd == 2) DGR_RENDER_BWD(2); else DGR_RENDER_BWD(1);
 #undef DGR_RENDER_BWD
     }
-    DGR_KERNEL("preprocess_bwd", st, s->debug, DGR_DISPATCH(launch_pre_bwd, s, g, radii, grad_rec, gout, st));
+    DGR_KERNEL("preprocess_bwd", st, s->debug, DGR_DISPATCH(launch_pre_bwd, s, g, radii, reinterpret_cast<const unsigned *>(geom + GL.off_touched), grad_rec, gout, st));
     return 0;
 }
 

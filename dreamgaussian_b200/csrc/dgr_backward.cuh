@@ -9,29 +9,27 @@
 
 namespace dgr {
 
-template <int DEG>
-__device__ __forceinline__ void sh_basis_grad(float x, float y, float z, float (&dbx)[16], float (&dby)[16], float (&dbz)[16]) {
-#pragma unroll
-    for (int i = 0; i < 16; i++) { dbx[i] = 0.f; dby[i] = 0.f; dbz[i] = 0.f; }
-    if (DEG > 0) {
-        dby[1] = -DGR_SH_C1; dbz[2] = DGR_SH_C1; dbx[3] = -DGR_SH_C1;
-        if (DEG > 1) {
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            dbx[4] = DGR_SH_C2_0 * y; dby[4] = DGR_SH_C2_0 * x;
-            dby[5] = DGR_SH_C2_1 * z; dbz[5] = DGR_SH_C2_1 * y;
-            dbx[6] = DGR_SH_C2_2 * -2.f * x; dby[6] = DGR_SH_C2_2 * -2.f * y; dbz[6] = DGR_SH_C2_2 * 4.f * z;
-            dbx[7] = DGR_SH_C2_3 * z; dbz[7] = DGR_SH_C2_3 * x;
-            dbx[8] = DGR_SH_C2_4 * 2.f * x; dby[8] = DGR_SH_C2_4 * -2.f * y;
-            if (DEG > 2) {
-                dbx[9] = DGR_SH_C3_0 * 6.f * xy; dby[9] = DGR_SH_C3_0 * (3.f * xx - 3.f * yy);
-                dbx[10] = DGR_SH_C3_1 * yz; dby[10] = DGR_SH_C3_1 * xz; dbz[10] = DGR_SH_C3_1 * xy;
-                dbx[11] = DGR_SH_C3_2 * -2.f * xy; dby[11] = DGR_SH_C3_2 * (4.f * zz - xx - 3.f * yy); dbz[11] = DGR_SH_C3_2 * 8.f * yz;
-                dbx[12] = DGR_SH_C3_3 * -6.f * xz; dby[12] = DGR_SH_C3_3 * -6.f * yz; dbz[12] = DGR_SH_C3_3 * (6.f * zz - 3.f * xx - 3.f * yy);
-                dbx[13] = DGR_SH_C3_4 * (4.f * zz - 3.f * xx - yy); dby[13] = DGR_SH_C3_4 * -2.f * xy; dbz[13] = DGR_SH_C3_4 * 8.f * xz;
-                dbx[14] = DGR_SH_C3_5 * 2.f * xz; dby[14] = DGR_SH_C3_5 * -2.f * yz; dbz[14] = DGR_SH_C3_5 * (xx - yy);
-                dbx[15] = DGR_SH_C3_6 * (3.f * xx - 3.f * yy); dby[15] = DGR_SH_C3_6 * -6.f * xy;
-            }
-        }
+// d basis_k / d(x, y, z) for one coefficient index (k is a compile-time constant after unrolling)
+__device__ __forceinline__ void sh_dbasis(int k, float x, float y, float z, float &dx, float &dy, float &dz) {
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    dx = 0.f; dy = 0.f; dz = 0.f;
+    switch (k) {
+        case 1: dy = -DGR_SH_C1; break;
+        case 2: dz = DGR_SH_C1; break;
+        case 3: dx = -DGR_SH_C1; break;
+        case 4: dx = DGR_SH_C2_0 * y; dy = DGR_SH_C2_0 * x; break;
+        case 5: dy = DGR_SH_C2_1 * z; dz = DGR_SH_C2_1 * y; break;
+        case 6: dx = DGR_SH_C2_2 * -2.f * x; dy = DGR_SH_C2_2 * -2.f * y; dz = DGR_SH_C2_2 * 4.f * z; break;
+        case 7: dx = DGR_SH_C2_3 * z; dz = DGR_SH_C2_3 * x; break;
+        case 8: dx = DGR_SH_C2_4 * 2.f * x; dy = DGR_SH_C2_4 * -2.f * y; break;
+        case 9: dx = DGR_SH_C3_0 * 6.f * xy; dy = DGR_SH_C3_0 * (3.f * xx - 3.f * yy); break;
+        case 10: dx = DGR_SH_C3_1 * yz; dy = DGR_SH_C3_1 * xz; dz = DGR_SH_C3_1 * xy; break;
+        case 11: dx = DGR_SH_C3_2 * -2.f * xy; dy = DGR_SH_C3_2 * (4.f * zz - xx - 3.f * yy); dz = DGR_SH_C3_2 * 8.f * yz; break;
+        case 12: dx = DGR_SH_C3_3 * -6.f * xz; dy = DGR_SH_C3_3 * -6.f * yz; dz = DGR_SH_C3_3 * (6.f * zz - 3.f * xx - 3.f * yy); break;
+        case 13: dx = DGR_SH_C3_4 * (4.f * zz - 3.f * xx - yy); dy = DGR_SH_C3_4 * -2.f * xy; dz = DGR_SH_C3_4 * 8.f * xz; break;
+        case 14: dx = DGR_SH_C3_5 * 2.f * xz; dy = DGR_SH_C3_5 * -2.f * yz; dz = DGR_SH_C3_5 * (xx - yy); break;
+        case 15: dx = DGR_SH_C3_6 * (3.f * xx - 3.f * yy); dy = DGR_SH_C3_6 * -6.f * xy; break;
+        default: break;
     }
 }
 
@@ -77,14 +75,14 @@ __device__ __forceinline__ void store_sh_grads(float *__restrict__ dL_dshs, int 
 }
 
 template <int DEG, bool HAS_SH, bool HAS_COV>
-__global__ void __launch_bounds__(kPreThreads)
+__global__ void __launch_bounds__(kPreThreads, 4)
 preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, float scale_modifier,
                       const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
                       const float *__restrict__ campos,
                       const float *__restrict__ means3D, const float *__restrict__ shs,
                       const float *__restrict__ opacities, const float *__restrict__ scales,
                       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
-                      const int *__restrict__ radii, const float *__restrict__ grad_rec,
+                      const int *__restrict__ radii, const unsigned *__restrict__ touched, const float *__restrict__ grad_rec,
                       float *__restrict__ dL_dmeans3D, float *__restrict__ dL_dmeans2D, float *__restrict__ dL_dshs,
                       float *__restrict__ dL_dcolors, float *__restrict__ dL_dopacities, float *__restrict__ dL_dscales,
                       float *__restrict__ dL_drotations, float *__restrict__ dL_dcov3D, int accumulate) {
@@ -94,7 +92,6 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
     __syncthreads();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const bool acc = accumulate != 0;
-    constexpr int NB = (DEG + 1) * (DEG + 1);
     const bool in_range = g < P;
     const bool visible = in_range && radii[g] > 0;
     float bs[16];
@@ -169,21 +166,15 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
             const float il = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
             dx *= il; dy *= il; dz *= il;
             sh_basis<DEG>(dx, dy, dz, bs);
-            float cf[48];
-            load_sh_row<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, cf);
-            float rgb[3] = { 0.f, 0.f, 0.f };
+            const unsigned flags = __ldg(touched + g) >> 29;              // SH channels the forward clamped at 0
 #pragma unroll
-            for (int k = 0; k < NB; k++) { rgb[0] += bs[k] * cf[3 * k]; rgb[1] += bs[k] * cf[3 * k + 1]; rgb[2] += bs[k] * cf[3 * k + 2]; }
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) gr[ch] = (rgb[ch] + DGR_SH_OFFSET < 0.f) ? 0.f : g_rgb[ch];
-            float dbx[16], dby[16], dbz[16];
-            sh_basis_grad<DEG>(dx, dy, dz, dbx, dby, dbz);
+            for (int ch = 0; ch < 3; ch++) gr[ch] = ((flags >> ch) & 1u) ? 0.f : g_rgb[ch];
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-#pragma unroll
-            for (int k = 0; k < NB; k++) {
-                const float dotc = cf[3 * k] * gr[0] + cf[3 * k + 1] * gr[1] + cf[3 * k + 2] * gr[2];
-                ddx += dbx[k] * dotc; ddy += dby[k] * dotc; ddz += dbz[k] * dotc;
-            }
+            for_each_sh_coeff<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, [&](int k, float c0, float c1, float c2) {
+                const float dotc = c0 * gr[0] + c1 * gr[1] + c2 * gr[2];
+                float bx, by, bz;
+                sh_dbasis(k, dx, dy, dz, bx, by, bz);
+                ddx += bx * dotc; ddy += by * dotc; ddz += bz * dotc; });
             const float dot = dx * ddx + dy * ddy + dz * ddz;
             dmean[0] += (ddx - dx * dot) * il; dmean[1] += (ddy - dy * dot) * il; dmean[2] += (ddz - dz * dot) * il;
         } else if (dL_dcolors) {

@@ -83,6 +83,10 @@ __device__ __forceinline__ int order_bin(unsigned count) {
 // One CTA: exclusive scan of the per-tile instance counts -> ranges (clipped to `cap`), total -> header; plus the
 // heaviest-first issue order of the render kernels (counting sort on log-scale population classes — longest
 // processing time first keeps the big tiles off the tail) and the list of tiles too big for the per-tile sort CTA.
+// One CTA of 1024 threads.  Every thread owns kScanTPT consecutive tiles in registers (up to 8192 tiles in one pass, more
+// in further passes): one global read of the counts, one block scan, then ranges / issue order / big-tile list.
+constexpr int kScanTPT = 8;
+
 __device__ __forceinline__ void
 tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long long cap, uint2 *__restrict__ ranges,
               GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order, TileWork *__restrict__ work,
@@ -94,37 +98,46 @@ tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
     if (tid == 0) { s_carry = 0; s_nbig = 0; }
     if (tid < kOrderBins) s_bin[tid] = 0;
     __syncthreads();
-    for (int base = 0; base < tiles; base += 1024) {
-        const int t = base + tid;
-        const unsigned long long v = (t < tiles) ? __ldcg(tile_count + t) : 0u;
-        unsigned long long inc = v;
+    const int span = 1024 * kScanTPT;
+    for (int base = 0; base < tiles; base += span) {
+        unsigned cnt[kScanTPT];
+        unsigned long long sum = 0;
+        const int t0 = base + tid * kScanTPT;
+#pragma unroll
+        for (int j = 0; j < kScanTPT; j++) { cnt[j] = (t0 + j < tiles) ? __ldcg(tile_count + t0 + j) : 0u; sum += cnt[j]; }
+        unsigned long long inc = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
-        if (lane == 31) s_warp[warp] = inc;                              // warp totals
+        if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
         if (warp == 0) {
             const unsigned long long w = s_warp[lane];
             unsigned long long winc = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += n; }
-            s_warp[lane] = winc - w;                                     // exclusive warp offsets
+            s_warp[lane] = winc - w;
             if (lane == 31) s_total = winc;
         }
         __syncthreads();
-        const unsigned long long excl = s_carry + s_warp[warp] + (inc - v);
-        if (t < tiles) {
-            const unsigned long long s = excl < cap ? excl : cap;
-            const unsigned long long e = (excl + v) < cap ? (excl + v) : cap;
-            ranges[t] = make_uint2((unsigned)s, (unsigned)e);
-            atomicAdd(&s_bin[order_bin((unsigned)(e - s))], 1u);
-            if ((unsigned)(e - s) > (unsigned)kSortSmallCap) big_list[atomicAdd(&s_nbig, 1u)] = (unsigned)t;
+        unsigned long long run = s_carry + s_warp[warp] + (inc - sum);
+#pragma unroll
+        for (int j = 0; j < kScanTPT; j++) {
+            if (t0 + j < tiles) {
+                const unsigned long long s = run < cap ? run : cap;
+                const unsigned long long e = (run + cnt[j]) < cap ? (run + cnt[j]) : cap;
+                ranges[t0 + j] = make_uint2((unsigned)s, (unsigned)e);
+                const unsigned pop = (unsigned)(e - s);                       // clipped population
+                atomicAdd(&s_bin[order_bin(pop)], 1u);
+                if (pop > (unsigned)kSortSmallCap) big_list[atomicAdd(&s_nbig, 1u)] = (unsigned)(t0 + j);
+            }
+            run += cnt[j];
         }
         __syncthreads();
         if (tid == 0) s_carry += s_total;
         __syncthreads();
     }
     if (tid == 0) { hdr->n_inst = s_carry; hdr->n_big = s_nbig; work->n_big = s_nbig; }
-    // counting sort of the tiles by population class
+    // counting sort of the tiles by population class (heaviest first)
     if (warp == 0) {
         unsigned run = 0;
         for (int b0 = 0; b0 < kOrderBins; b0 += 32) {
@@ -143,6 +156,15 @@ tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
     }
 }
 
+// Stand-alone tile scan: used when stage 2 is re-run with a larger capacity (the column scan must not run twice: it
+// rewrote the count matrix in place; the column totals in tile_count are still valid).
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int tiles, const unsigned *__restrict__ tile_count, unsigned long long cap, uint2 *__restrict__ ranges,
+                 GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order, TileWork *__restrict__ work,
+                 unsigned *__restrict__ big_list) {
+    tile_scan_cta(tiles, tile_count, cap, ranges, hdr, tile_order, work, big_list);
+}
+
 // Column scan of the [nblocks x tiles] count matrix (in place -> exclusive per-(block, tile) offsets) + column totals.
 // One CTA = 32 tiles (lanes, coalesced 128-byte rows) x 32 block-groups (warps): every thread first sums its slice of
 // the column, the 32 partial sums are scanned through shared memory, then the slice is rewritten as running offsets.
@@ -156,26 +178,41 @@ tile_colscan_kernel(int tiles, int nblocks, unsigned *__restrict__ blk_hist, uns
     const int t = blockIdx.x * 32 + lane;
     const int per = (nblocks + 31) / 32;
     const int b0 = grp * per, b1 = min(nblocks, b0 + per);
+    constexpr int kRegRows = 16;                    // slices of up to 16 rows stay in registers: the matrix is read once
+    unsigned v[kRegRows];
     unsigned sum = 0;
+    const bool in_regs = per <= kRegRows;
     if (t < tiles) {
         const unsigned *p = blk_hist + t;
+        if (in_regs) {
+#pragma unroll
+            for (int j = 0; j < kRegRows; j++) { v[j] = (b0 + j < b1) ? p[(size_t)(b0 + j) * tiles] : 0u; }
+#pragma unroll
+            for (int j = 0; j < kRegRows; j++) sum += v[j];
+        } else {
 #pragma unroll 4
-        for (int b = b0; b < b1; b++) sum += p[(size_t)b * tiles];
+            for (int b = b0; b < b1; b++) sum += p[(size_t)b * tiles];
+        }
     }
     s_part[grp][lane] = sum;
     __syncthreads();
     if (grp == 0) {                       // one warp: exclusive scan over the 32 groups of each tile (lane = tile)
         unsigned run = 0;
 #pragma unroll
-        for (int g = 0; g < 32; g++) { const unsigned v = s_part[g][lane]; s_part[g][lane] = run; run += v; }
+        for (int g = 0; g < 32; g++) { const unsigned x = s_part[g][lane]; s_part[g][lane] = run; run += x; }
         if (t < tiles) tile_count[t] = run;
     }
     __syncthreads();
     if (t < tiles) {
         unsigned run = s_part[grp][lane];
         unsigned *p = blk_hist + t;
+        if (in_regs) {
+#pragma unroll
+            for (int j = 0; j < kRegRows; j++) { if (b0 + j < b1) p[(size_t)(b0 + j) * tiles] = run; run += v[j]; }
+        } else {
 #pragma unroll 4
-        for (int b = b0; b < b1; b++) { const unsigned c = p[(size_t)b * tiles]; p[(size_t)b * tiles] = run; run += c; }
+            for (int b = b0; b < b1; b++) { const unsigned c = p[(size_t)b * tiles]; p[(size_t)b * tiles] = run; run += c; }
+        }
     }
     // the last CTA to finish turns the column totals into tile ranges (saves a launch and its round trip)
     __threadfence();
@@ -202,13 +239,21 @@ emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, const Rec *__rest
     for (int it = 0; it < gpb_iters; it++) {
         const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + threadIdx.x);
         if (g >= P) continue;
-        if (touched[g] == 0) continue;
+        if ((touched[g] & 0x1fffffffu) == 0) continue;
         const float4 q1 = rec[g].q1;
         const unsigned long long key = ((unsigned long long)__float_as_uint(q1.z) << 32) | (unsigned)g;
-        for_each_touched_tile(__float_as_uint(q1.w), __float_as_uint(rec[g].q2.w), gx, [&](int t) {
+        const unsigned ax = __float_as_uint(q1.w), ay = __float_as_uint(rec[g].q2.w);
+        const int tx0 = (int)(ax & 0xffffu) >> 4, tw = ((int)(ax >> 16) >> 4) - tx0 + 1;
+        const int ty0 = (int)(ay & 0xffffu) >> 4;
+        const int cnt = (int)(touched[g] & 0x1fffffffu);                  // = tw * th (same AABB as the histogram)
+        int x = 0, t = ty0 * gx + tx0;
+#pragma unroll 4
+        for (int i = 0; i < cnt; i++) {
             const unsigned pos = atomicAdd(&s_off[t], 1u);
             if (pos < __ldg(&ranges[t].y)) keys[pos] = key;               // beyond the (clipped) range: dropped
-        });
+            x++; t++;
+            if (x == tw) { x = 0; t += gx - tw; }
+        }
     }
 }
 

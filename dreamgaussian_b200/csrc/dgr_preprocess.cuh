@@ -64,25 +64,31 @@ __device__ __forceinline__ void sh_basis(float x, float y, float z, float (&b)[1
     }
 }
 
-// Load the first 3*(DEG+1)^2 floats of one Gaussian's SH row ([M][3] layout) with 128-bit loads when the row is
-// 16-byte aligned (M % 4 == 0: the deg-1 and deg-3 tensors), scalar otherwise.
-template <int DEG>
-__device__ __forceinline__ void load_sh_row(const float *row, bool vec, float (&c)[48]) {
-    constexpr int NF = 3 * (DEG + 1) * (DEG + 1);
-    if (vec) {
+// Streams one Gaussian's SH row ([M][3] layout) in chunks of 8 coefficients (6 x 128-bit loads in flight when the row is
+// 16-byte aligned, i.e. M % 4 == 0: the deg-1 and deg-3 tensors; scalar loads otherwise) and hands every coefficient to f.
+// Keeping only one chunk live (instead of all 48 floats) is what keeps the per-Gaussian kernels below 64 registers.
+template <int DEG, class F>
+__device__ __forceinline__ void for_each_sh_coeff(const float *row, bool vec, F f) {
+    constexpr int NB = (DEG + 1) * (DEG + 1);
 #pragma unroll
-        for (int i = 0; i < (NF + 3) / 4; i++) {
-            if (4 * i + 3 < NF) {
-                const float4 v = ldg_f4(row + 4 * i);
-                c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
-            } else {
+    for (int k0 = 0; k0 < NB; k0 += 8) {
+        constexpr int dummy = 0; (void)dummy;
+        const int n = (NB - k0) < 8 ? (NB - k0) : 8;        // compile-time after unrolling
+        float c[24];
+        if (vec) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) if (4 * i + j < NF) c[4 * i + j] = __ldg(row + 4 * i + j);
+            for (int i = 0; i < 6; i++) {
+                if (4 * i < 3 * n) {
+                    const float4 v = ldg_f4(row + 3 * k0 + 4 * i);
+                    c[4 * i] = v.x; c[4 * i + 1] = v.y; c[4 * i + 2] = v.z; c[4 * i + 3] = v.w;
+                }
             }
-        }
-    } else {
+        } else {
 #pragma unroll
-        for (int i = 0; i < NF; i++) c[i] = __ldg(row + i);
+            for (int i = 0; i < 24; i++) if (i < 3 * n) c[i] = __ldg(row + 3 * k0 + i);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (j < n) f(k0 + j, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
     }
 }
 
@@ -131,7 +137,7 @@ __device__ __forceinline__ void project_geo(const FrameConsts &fc, const float3 
 }
 
 template <int DEG, bool HAS_SH, bool HAS_COV>
-__global__ void __launch_bounds__(kPreThreads)
+__global__ void __launch_bounds__(kPreThreads, 4)
 preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, float scale_modifier,
                       const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
                       const float *__restrict__ campos,
@@ -151,7 +157,7 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
     __syncthreads();
     for (int it = 0; it < gpb_iters; it++) {
     const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + threadIdx.x);
-    unsigned touched = 0;
+    unsigned touched = 0, clamp_flags = 0;
     if (g < P) {
         int radius_out = 0;
         Rec r;
@@ -197,12 +203,13 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                         const float il = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
                         dx *= il; dy *= il; dz *= il;
                         float b[16]; sh_basis<DEG>(dx, dy, dz, b);
-                        float c[48];
-                        load_sh_row<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, c);
                         cr = 0.f; cg = 0.f; cb = 0.f;
-#pragma unroll
-                        for (int k = 0; k < (DEG + 1) * (DEG + 1); k++) { cr += b[k] * c[3 * k]; cg += b[k] * c[3 * k + 1]; cb += b[k] * c[3 * k + 2]; }
-                        cr = fmaxf(cr + DGR_SH_OFFSET, 0.f); cg = fmaxf(cg + DGR_SH_OFFSET, 0.f); cb = fmaxf(cb + DGR_SH_OFFSET, 0.f);
+                        for_each_sh_coeff<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, [&](int k, float c0, float c1, float c2) {
+                            cr += b[k] * c0; cg += b[k] * c1; cb += b[k] * c2; });
+                        cr += DGR_SH_OFFSET; cg += DGR_SH_OFFSET; cb += DGR_SH_OFFSET;
+                        // channels clamped at 0 get no colour gradient: remembered in the top bits of `touched`
+                        clamp_flags = (cr < 0.f ? 1u : 0u) | (cg < 0.f ? 2u : 0u) | (cb < 0.f ? 4u : 0u);
+                        cr = fmaxf(cr, 0.f); cg = fmaxf(cg, 0.f); cb = fmaxf(cb, 0.f);
                     } else {
                         cr = __ldg(colors_precomp + 3 * (size_t)g); cg = __ldg(colors_precomp + 3 * (size_t)g + 1); cb = __ldg(colors_precomp + 3 * (size_t)g + 2);
                     }
@@ -234,7 +241,7 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
         }
         radii[g] = radius_out;
         rec[g] = r;
-        touched_out[g] = touched;
+        touched_out[g] = touched | (clamp_flags << 29);     // tiles touched (29 bits) | SH clamp flags (3 bits)
     }
     }
     __syncthreads();

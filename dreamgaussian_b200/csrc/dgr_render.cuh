@@ -312,14 +312,15 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     }
     for (int k = 0; k < nchunks; k++) {
         const int c = nchunks - 1 - k, s = k % kStages;
+        // Every warp observes EVERY phase of the full barrier, also for chunks it does not need: a warp that skipped the
+        // wait could come back to this stage while the barrier is still one phase behind and the parity test would alias.
+        mbar_wait(&sm.full[s], (uint32_t)((k / kStages) & 1));
         if ((unsigned)(c * kChunk) >= wlast) {
             // nothing of this chunk reaches this warp's pixels: hand the stage back without touching the data
-            if (k >= kStages) mbar_wait(&sm.empty[s], (uint32_t)(((k / kStages) - 1) & 1));
             if (lane == 0) mbar_arrive(&sm.empty[s]);
             __syncwarp();
             continue;
         }
-        mbar_wait(&sm.full[s], (uint32_t)((k / kStages) & 1));
         const int cnt = min(kChunk, n - c * kChunk);
         for (int b = ((cnt - 1) >> 5) << 5; b >= 0; b -= 32) {
             if ((unsigned)(c * kChunk + b) >= wlast) continue;

@@ -125,10 +125,11 @@ def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, 
         out = _lib.DgrImages(_ptr(color), _ptr(depth), _ptr(alpha), _ptr(radii))
         key = (dev.index, P, H, W)
         cap, big = _CAPACITY_HINT.get(key, (max(65536, 16 * P), True))
+        rerun = 0
         while True:
             binning = torch.empty((lib.dgr_binning_bytes(cap, H, W),), **u8)
             _lib.check(lib.dgr_forward_render(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(binning),
-                                              ctypes.c_uint64(cap), _ptr(image), ctypes.byref(out), 1 if big else 0,
+                                              ctypes.c_uint64(cap), _ptr(image), ctypes.byref(out), (1 if big else 0) | rerun,
                                               ctypes.c_void_p(n_host.data_ptr()), event, st))
             _lib.check(lib.dgr_event_synchronize(event))
             n_inst, n_big = int(n_host[0]), int(n_host[1])
@@ -136,6 +137,7 @@ def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, 
                 break
             cap = max(cap, int(n_inst * 1.25) + 4096)  # a guess was wrong: redo stage 2 (rare)
             big = big or n_big > 0
+            rerun = 2                                   # DGR_FLAG_RERUN
         _CAPACITY_HINT[key] = (max(int(n_inst * 1.25) + 4096, 65536), n_big > 0)
     state = ForwardState()
     state.rs, state.frame, state.num_rendered, state.capacity = rs, fr, n_inst, cap

@@ -100,8 +100,10 @@ int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *ge
  * asynchronously right after the scan: counts_host[0] = instance count, counts_host[1] = number of big tiles; if
  * count_ready_event != NULL (from dgr_event_create) it is recorded at that point, so the caller keeps enqueuing work and
  * checks the guesses once that event has fired.  If counts_host[0] > capacity_instances, or counts_host[1] > 0 without
- * DGR_FLAG_BIG_TILES, the call produced a memory-safe but wrong image: re-run stage 2 with corrected guesses. */
+ * DGR_FLAG_BIG_TILES, the call produced a memory-safe but wrong image: re-run stage 2 with corrected guesses and
+ * DGR_FLAG_RERUN set. */
 #define DGR_FLAG_BIG_TILES 1
+#define DGR_FLAG_RERUN 2      /* set when stage 2 is repeated for the same stage 1 (corrected guesses) */
 int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom, void *binning,
                        uint64_t capacity_instances, void *image, const DgrImages *out, int32_t flags,
                        uint64_t *counts_host, void *count_ready_event, void *stream);

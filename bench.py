@@ -29,8 +29,8 @@ import numpy as np  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=100000)
     ap.add_argument("--res", type=int, default=800)
@@ -89,7 +89,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def wait_first_sample(self, timeout=3.0):
+        """nvidia-smi needs ~100 ms to start: block until it has produced a row so a short run is still covered."""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        return len(self.rows)
+
+    def stop(self, window=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -99,7 +108,10 @@ class ClockSampler:
             pass
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows, where = self.rows, "whole run (timed region shorter than the 20 ms sampling period)"
+        if window and window[1] - window[0] >= 3:
+            rows, where = self.rows[window[0]:window[1]], "timed region"
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -111,7 +123,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": where}
 
 
 def build_scene(a):
@@ -219,6 +231,7 @@ def run_ours(a, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
     for i in range(a.warmup):
         step(i)
     barrier()
@@ -227,6 +240,7 @@ def run_ours(a, rank, world, local_rank):
     lib.dgr_reset_launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     barrier()
+    mark0 = sampler.mark()
     wall0 = time.perf_counter()
     for i in range(a.steps):
         flush_buf.zero_()
@@ -236,7 +250,7 @@ def run_ours(a, rank, world, local_rank):
     barrier()
     wall1 = time.perf_counter()
     launches = int(lib.dgr_launch_count())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop((mark0, sampler.mark())) if rank == 0 else None
     ms_local = sum(e0.elapsed_time(e1) for e0, e1 in evs)
     ms_t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
     if world > 1:
@@ -266,52 +280,102 @@ def run_ours(a, rank, world, local_rank):
         barrier()
 
     # ---------------- end to end through the public API with HOST buffers ----------------
+    # Every step copies ALL Gaussian inputs from pinned host memory to the device, runs GaussianRasterizer forward +
+    # autograd backward, and copies the loss and ALL input gradients back to pinned host memory.  The three legs run on
+    # three streams over a ring of 3 buffer sets, so step i's compute overlaps step i+1's upload and step i-1's download
+    # (PCIe is full duplex); every byte of every step is moved inside the timed region.
     e2e = None
     if not a.no_e2e:
-        host = {k: torch.tensor(v).pin_memory() for k, v in cloud.items()}
-        grads_host = {k: torch.empty_like(v).pin_memory() for k, v in host.items()}
-        loss_host = torch.zeros((1,), dtype=torch.float32).pin_memory()
+        names = ("means3D", "shs", "opacities", "scales", "rotations")
+        host = {k: torch.tensor(cloud[k]).pin_memory() for k in names}
+        RING = 3
+        dev_in = [{k: torch.empty_like(host[k], device=dev).requires_grad_(True) for k in names} for _ in range(RING)]
+        grads_host = [{k: torch.empty_like(host[k]).pin_memory() for k in names} for _ in range(RING)]
+        loss_host = [torch.zeros((1,), dtype=torch.float32).pin_memory() for _ in range(RING)]
         h2d = sum(v.numel() * 4 for v in host.values())
-        d2h = sum(v.numel() * 4 for v in grads_host.values()) + 4
+        d2h = h2d + 4
+        s_up, s_comp, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        ev_up = [torch.cuda.Event() for _ in range(RING)]
+        ev_comp = [torch.cuda.Event() for _ in range(RING)]
+        ev_down = [torch.cuda.Event() for _ in range(RING)]
+        m2d = torch.zeros((P, 3), device=dev)
 
-        def e2e_step(i):
+        def upload(i):
+            r = i % RING
+            with torch.cuda.stream(s_up):
+                s_up.wait_event(ev_comp[r])                 # the previous user of this buffer set has finished computing
+                with torch.no_grad():
+                    for k in names:
+                        dev_in[r][k].copy_(host[k], non_blocking=True)
+                ev_up[r].record(s_up)
+
+        def compute(i):
+            r = i % RING
             v = (i * world + rank) % len(settings)
-            dvc = {k: hv.to(dev, non_blocking=True).requires_grad_(True) for k, hv in host.items()}
-            m2d = torch.zeros((P, 3), device=dev, requires_grad=True)
-            color, radii, depth, alpha = GaussianRasterizer(raster_settings=settings[v])(
-                means3D=dvc["means3D"], means2D=m2d, shs=dvc["shs"], opacities=dvc["opacities"], scales=dvc["scales"],
-                rotations=dvc["rotations"])
-            gC, _, gA = ups_d[v % len(ups_d)]
-            loss = (color * gC).sum() + (alpha * gA).sum()
-            loss.backward()
-            if world > 1:
-                flat = torch.cat([dvc[k].grad.reshape(-1) for k in ("means3D", "shs", "opacities", "scales", "rotations")])
-                dist.all_reduce(flat)
-                o = 0
-                for k in ("means3D", "shs", "opacities", "scales", "rotations"):
-                    n = dvc[k].grad.numel()
-                    grads_host[k].copy_(flat[o:o + n].view_as(grads_host[k]), non_blocking=True); o += n
-            else:
-                for k in grads_host:
-                    grads_host[k].copy_(dvc[k].grad, non_blocking=True)
-            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            with torch.cuda.stream(s_comp):
+                s_comp.wait_event(ev_up[r])
+                s_comp.wait_event(ev_down[r])               # its gradients of RING steps ago have been downloaded
+                for k in names:
+                    dev_in[r][k].grad = None
+                color, radii, depth, alpha = GaussianRasterizer(raster_settings=settings[v])(
+                    means3D=dev_in[r]["means3D"], means2D=m2d, shs=dev_in[r]["shs"], opacities=dev_in[r]["opacities"],
+                    scales=dev_in[r]["scales"], rotations=dev_in[r]["rotations"])
+                gC, _, gA = ups_d[v % len(ups_d)]
+                loss = (color * gC).sum() + (alpha * gA).sum()
+                loss.backward()
+                if world > 1:
+                    flat = torch.cat([dev_in[r][k].grad.reshape(-1) for k in names])
+                    dist.all_reduce(flat)
+                    o = 0
+                    for k in names:
+                        n = dev_in[r][k].grad.numel()
+                        dev_in[r][k].grad.copy_(flat[o:o + n].view_as(dev_in[r][k].grad)); o += n
+                ev_comp[r].record(s_comp)
+                return loss.detach()
 
-        for i in range(max(3, min(a.warmup, 3))):
-            e2e_step(i)
+        def download(i, loss):
+            r = i % RING
+            with torch.cuda.stream(s_down):
+                s_down.wait_event(ev_comp[r])
+                for k in names:
+                    g = dev_in[r][k].grad
+                    g.record_stream(s_down)
+                    grads_host[r][k].copy_(g, non_blocking=True)
+                loss.record_stream(s_down)
+                loss_host[r].copy_(loss.reshape(1), non_blocking=True)
+                ev_down[r].record(s_down)
+
+        def run(nsteps, first):
+            upload(first)
+            for i in range(first, first + nsteps):
+                if i + 1 < first + nsteps:
+                    upload(i + 1)
+                ls = compute(i)
+                download(i, ls)
+
+        for r in range(RING):
+            ev_comp[r].record(s_comp); ev_down[r].record(s_down)
+        run(max(3, min(a.warmup, 6)), 0)
         barrier()
+        e2e_steps = min(a.steps, 300)
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(a.steps):
-            e2e_step(i)
+        e0.record()                                          # default stream: ordered before the side streams by barrier()
+        for st_ in (s_up, s_comp, s_down):
+            st_.wait_event(e0)
+        run(e2e_steps, 100)
+        for st_ in (s_up, s_comp, s_down):
+            torch.cuda.current_stream(dev).wait_stream(st_)
         e1.record()
         barrier()
         ms_e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": P * world * a.steps / (float(ms_e.item()) * 1e-3), "unit": "splats/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": float(ms_e.item()) / a.steps,
-               "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / a.steps}
+        e2e = {"value": P * world * e2e_steps / (float(ms_e.item()) * 1e-3), "unit": "splats/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": float(ms_e.item()) / e2e_steps, "steps": e2e_steps,
+               "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / e2e_steps,
+               "note": "public API (GaussianRasterizer + autograd); inputs from / gradients + loss to pinned host memory every step; "
+                       "upload, compute and download of consecutive steps overlap on 3 streams"}
 
     if rank != 0:
         return

@@ -144,6 +144,15 @@ __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched
 
 bool g_sort_attr_set = false;
 int g_big_grid = 148;
+int g_snake = 1;
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return g_snake ? n : (1 << 30);      // a huge "SM count" disables the snake (no complete round)
+}
 // tuning knobs (dgr_set_tuning): pixels per lane of the render kernels, heaviest-first tile order on/off
 int g_ppl_fwd = 1, g_ppl_bwd = 2;
 bool g_no_order = false;
@@ -181,7 +190,7 @@ int dgr_profile_collect(char *names, size_t names_bytes, float *ms, int max) {
 
 int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order) {
     if ((ppl_fwd != 1 && ppl_fwd != 2 && ppl_fwd != 4) || (ppl_bwd != 1 && ppl_bwd != 2 && ppl_bwd != 4)) return fail(-1, "ppl must be 1, 2 or 4");
-    g_ppl_fwd = ppl_fwd; g_ppl_bwd = ppl_bwd; g_no_order = tile_order == 0;
+    g_ppl_fwd = ppl_fwd; g_ppl_bwd = ppl_bwd; g_no_order = tile_order == 0; g_snake = tile_order != 2;
     return 0;
 }
 
@@ -249,11 +258,11 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
     TileWork *work = reinterpret_cast<TileWork *>(image + IL.off_work);
     if (flags & DGR_FLAG_RERUN)
         DGR_KERNEL("tile_scan", st, s->debug,
-                   tile_scan_kernel<<<1, 1024, 0, st>>>(tiles, tile_count, (unsigned long long)capacity, ranges, hdr, tile_order, work, big_list));
+                   tile_scan_kernel<<<1, 1024, 0, st>>>(tiles, tile_count, (unsigned long long)capacity, ranges, hdr, tile_order, work, big_list, sm_count()));
     else
         DGR_KERNEL("tile_colscan_scan", st, s->debug,
                    tile_colscan_kernel<<<(tiles + 31) / 32, 1024, 0, st>>>(tiles, GL.nblocks, blk_hist, tile_count, (unsigned long long)capacity,
-                                                                            ranges, hdr, tile_order, work, big_list));
+                                                                            ranges, hdr, tile_order, work, big_list, sm_count()));
     if (counts_host)      // { n_instances, n_big_tiles }
         DGR_CUDA(cudaMemcpyAsync(counts_host, geom, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     if (count_ready_event) DGR_CUDA(cudaEventRecord((cudaEvent_t)count_ready_event, st));

@@ -404,8 +404,8 @@ def run_ours(a, rank, world, local_rank):
         "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "views_per_gpu_per_step": 1, "view_set": a.views, "l2_flush_between_steps": True,
-                   "n_inst_view0": n_inst, "parallelism": "view-sharded dp%d, replicated Gaussians, 1 NCCL all-reduce of %d MB"
-                   % (world, vsr.grads.nbytes() >> 20) if world > 1 else "single GPU",
+                   "n_inst_view0": n_inst, "parallelism": "view-sharded dp%d, replicated Gaussians, 1 all-reduce of %d MB per step (%s)"
+                   % (world, vsr.grads.nbytes() >> 20, vsr.collective) if world > 1 else "single GPU",
                    "wall_ms_per_step_incl_flush": (wall1 - wall0) * 1e3 / a.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e,
     }

@@ -48,7 +48,7 @@ EXPORTS = (
     "dgr_abi_version", "dgr_last_error", "dgr_launch_count", "dgr_reset_launch_count",
     "dgr_geom_bytes", "dgr_image_bytes", "dgr_binning_bytes",
     "dgr_forward_preprocess", "dgr_forward_render", "dgr_backward", "dgr_mark_visible", "dgr_debug_geom",
-    "dgr_profile_enable", "dgr_profile_collect", "dgr_event_create", "dgr_event_synchronize", "dgr_event_destroy", "dgr_set_tuning",
+    "dgr_profile_enable", "dgr_profile_collect", "dgr_event_create", "dgr_event_synchronize", "dgr_event_destroy", "dgr_set_tuning", "dgr_peer_allreduce",
 )
 
 _lib = None
@@ -86,6 +86,8 @@ def load():
     lib.dgr_binning_bytes.argtypes = [u64, i32, i32]
     lib.dgr_forward_preprocess.restype = ctypes.c_int
     lib.dgr_forward_preprocess.argtypes = [ctypes.POINTER(DgrSettings), ctypes.POINTER(DgrGaussians), vp, vp, vp, vp]
+    lib.dgr_peer_allreduce.restype = ctypes.c_int
+    lib.dgr_peer_allreduce.argtypes = [vp, i32, i32, u64, u64, vp]
     lib.dgr_set_tuning.restype = ctypes.c_int
     lib.dgr_set_tuning.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.dgr_event_create.restype = vp

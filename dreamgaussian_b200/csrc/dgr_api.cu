@@ -11,6 +11,7 @@
 #include "../../include/dgr_b200.h"
 #include "dgr_backward.cuh"
 #include "dgr_binning.cuh"
+#include "dgr_collective.cuh"
 #include "dgr_common.cuh"
 #include "dgr_preprocess.cuh"
 #include "dgr_render.cuh"
@@ -145,14 +146,15 @@ __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched
 bool g_sort_attr_set = false;
 int g_big_grid = 148;
 int g_snake = 1;
-int sm_count() {
+int sm_count_raw() {
     static int n = 0;
     if (n == 0) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     }
-    return g_snake ? n : (1 << 30);      // a huge "SM count" disables the snake (no complete round)
+    return n;
 }
+int sm_count() { return g_snake ? sm_count_raw() : (1 << 30); }      // a huge "SM count" disables the snake order
 // tuning knobs (dgr_set_tuning): pixels per lane of the render kernels, heaviest-first tile order on/off
 int g_ppl_fwd = 1, g_ppl_bwd = 2;
 bool g_no_order = false;
@@ -330,6 +332,28 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
 #undef DGR_RENDER_BWD
     }
     DGR_KERNEL("preprocess_bwd", st, s->debug, DGR_DISPATCH(launch_pre_bwd, s, g, radii, reinterpret_cast<const unsigned *>(geom + GL.off_touched), grad_rec, gout, st));
+    return 0;
+}
+
+int dgr_peer_allreduce(const uint64_t *peer_ptrs, int32_t world, int32_t rank, uint64_t n_floats, uint64_t multicast_ptr, void *stream) {
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(-1, "bad world / rank");
+    if (n_floats % 4 != 0) return fail(-1, "n_floats must be a multiple of 4");
+    if (!peer_ptrs && !multicast_ptr) return fail(-1, "no peer pointers");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n4 = (size_t)(n_floats / 4);
+    if (n4 == 0 || world == 1) return 0;
+    const size_t per = (n4 + world - 1) / world;
+    int grid = (int)((per + 511) / 512);
+    if (grid > 4 * sm_count_raw()) grid = 4 * sm_count_raw();
+    if (grid < 1) grid = 1;
+    if (multicast_ptr) {
+        DGR_KERNEL("allreduce_multimem", st, 0,
+                   allreduce_multimem_kernel<<<grid, 512, 0, st>>>(reinterpret_cast<float *>(multicast_ptr), world, rank, n4));
+    } else {
+        PeerPtrs pp;
+        for (int w = 0; w < kMaxPeers; w++) pp.p[w] = w < world ? reinterpret_cast<float *>(peer_ptrs[w]) : nullptr;
+        DGR_KERNEL("allreduce_p2p", st, 0, allreduce_p2p_kernel<<<grid, 512, 0, st>>>(pp, world, rank, n4));
+    }
     return 0;
 }
 

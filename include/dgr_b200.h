@@ -125,6 +125,14 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom, const 
                  uint64_t capacity_instances, const void *image, const int32_t *radii, const float *out_alpha,
                  const DgrImageGrads *gin, const DgrGaussianGrads *gout, void *stream);
 
+/* Multi-GPU (view-sharded data parallelism): all-reduce(sum) of the flat float32 gradient buffer over
+ * NVLink with this library's own kernel.  The buffer lives in symmetric memory: peer_ptrs[w] (HOST array of `world` device
+ * addresses) is rank w's copy mapped into this process; multicast_ptr, if non-zero, is the NVSwitch multicast address of
+ * the same buffer (then multimem.ld_reduce / multimem.st are used and peer_ptrs may be NULL).  n_floats % 4 == 0.
+ * The caller synchronises the ranks (device-side barrier) before and after the call. */
+int dgr_peer_allreduce(const uint64_t *peer_ptrs, int32_t world, int32_t rank, uint64_t n_floats, uint64_t multicast_ptr,
+                       void *stream);
+
 /* GaussianRasterizer.markVisible: present[i] = 1 if Gaussian i passes the near-plane test. */
 int dgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
                      uint8_t *present, void *stream);

@@ -51,8 +51,8 @@ __device__ __forceinline__ bool record_hits_subtile(const Rec &r, int wx0, int w
 // Sub-tile geometry of one consumer warp for PPL pixels per lane.
 template <int PPL>
 struct SubTile {
-    static constexpr int kWarps = 8 / PPL;                 // consumer warps per tile
-    static constexpr int kThreads = (kWarps + 1) * 32;     // + the producer warp
+    static constexpr int kWarps = 8 / PPL;                 // warps per tile (all of them consumers; warp 0 also feeds the ring)
+    static constexpr int kThreads = kWarps * 32;
     static constexpr int kW = (PPL == 4) ? 16 : 8;         // region width
     static constexpr int kH = (PPL == 1) ? 4 : 8;          // region height
     __device__ static __forceinline__ int x0(int tx, int warp) { return tx * kTile + ((PPL == 4) ? 0 : (warp & 1) * 8); }
@@ -93,30 +93,30 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     }
     __syncthreads();
 
-    if (warp == (int)NW) {
-        // ------------------------------- producer warp: one elected lane drives the TMA ring -------------------------------
-        if (lane == 0) {
-            int issued = 0;
-            for (int c = 0; c < nchunks; c++) {
-                const int st = c % kStages;
-                bool stop = false;
-                if (c >= kStages) {            // wait until every consumer warp released chunk c - kStages
-                    const uint32_t par = (uint32_t)(((c / kStages) - 1) & 1);
-                    while (!mbar_try_wait(&sm.empty[st], par)) { if (*vdone == NW) { stop = true; break; } }
-                }
-                if (stop || *vdone == NW) break;
-                const uint32_t bytes = (uint32_t)min(kChunk, n - c * kChunk) * (uint32_t)sizeof(Rec);
-                mbar_expect_tx(&sm.full[st], bytes);
-                tma_bulk_g2s(&sm.rec[st][0], src + (size_t)c * kChunk, bytes, &sm.full[st]);
-                issued = c + 1;
+    // Warp 0's lane 0 feeds the ring: at the top of chunk c it makes sure chunk c itself is in flight (blocking on the
+    // stage's "empty" barrier if it must) and then prefetches up to kStages - 1 chunks ahead without blocking.
+    int next_issue = 0;
+    auto issue = [&](int c) {
+        const int st = c % kStages;
+        const uint32_t bytes = (uint32_t)min(kChunk, n - c * kChunk) * (uint32_t)sizeof(Rec);
+        mbar_expect_tx(&sm.full[st], bytes);
+        tma_bulk_g2s(&sm.rec[st][0], src + (size_t)c * kChunk, bytes, &sm.full[st]);
+    };
+    auto produce = [&](int c) {          // returns false when every warp of the tile is finished
+        while (next_issue < nchunks && next_issue <= c) {
+            if (next_issue >= kStages) {
+                const uint32_t par = (uint32_t)(((next_issue / kStages) - 1) & 1);
+                while (!mbar_try_wait(&sm.empty[next_issue % kStages], par)) { if (*vdone == NW) return false; }
             }
-            // never leave the CTA with a bulk copy in flight into its shared memory
-            for (int cc = max(0, issued - kStages); cc < issued; cc++) mbar_wait(&sm.full[cc % kStages], (uint32_t)((cc / kStages) & 1));
+            issue(next_issue++);
         }
-        return;
-    }
+        while (next_issue < nchunks && next_issue < c + kStages) {
+            if (next_issue >= kStages && !mbar_try_wait(&sm.empty[next_issue % kStages], (uint32_t)(((next_issue / kStages) - 1) & 1))) break;
+            issue(next_issue++);
+        }
+        return true;
+    };
 
-    // ------------------------------------------------- consumer warps -------------------------------------------------
     const int wx0 = ST::x0(tx, warp), wy0 = ST::y0(ty, warp);
     const int wx1 = wx0 + ST::kW - 1, wy1 = wy0 + ST::kH - 1;
     float fx[PPL], fy[PPL], T[PPL], C0[PPL], C1[PPL], C2[PPL], D[PPL];
@@ -135,6 +135,11 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     if (warp_done && lane == 0) atomicAdd(&sm.done_warps, 1u);
     for (int c = 0; c < nchunks; c++) {
         const int s = c % kStages;
+        if (warp == 0) {
+            bool go = true;
+            if (lane == 0) go = produce(c);
+            if (!__shfl_sync(0xffffffffu, go ? 1 : 0, 0)) break;
+        }
         if (!warp_done) {
             mbar_wait(&sm.full[s], (uint32_t)((c / kStages) & 1));
             const int cnt = min(kChunk, n - c * kChunk);
@@ -192,6 +197,9 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
             __syncwarp();
         }
     }
+    // never leave the CTA with a bulk copy in flight into its shared memory
+    if (warp == 0 && lane == 0)
+        for (int cc = max(0, next_issue - kStages); cc < next_issue; cc++) mbar_wait(&sm.full[cc % kStages], (uint32_t)((cc / kStages) & 1));
 
     const float b0 = __ldg(bg), b1 = __ldg(bg + 1), b2 = __ldg(bg + 2);
     const size_t HW = (size_t)H * W;
@@ -250,8 +258,7 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint2 range = ranges[tile];
     if (range.y == range.x) return;
-    const bool producer = warp == (int)NW;
-    const int wx0 = ST::x0(tx, producer ? 0 : warp), wy0 = ST::y0(ty, producer ? 0 : warp);
+    const int wx0 = ST::x0(tx, warp), wy0 = ST::y0(ty, warp);
     const int wx1 = wx0 + ST::kW - 1, wy1 = wy0 + ST::kH - 1;
 
     float fx[PPL], fy[PPL], gc0[PPL], gc1[PPL], gc2[PPL], gd[PPL], ga[PPL], T[PPL], R[PPL];
@@ -264,7 +271,7 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
         const int x = ST::px(wx0, lane, p), y = ST::py(wy0, lane, p);
         fx[p] = (float)x; fy[p] = (float)y;
         gc0[p] = 0.f; gc1[p] = 0.f; gc2[p] = 0.f; gd[p] = 0.f; ga[p] = 0.f; T[p] = 1.f; last[p] = 0;
-        if (!producer && (x < W) && (y < H)) {
+        if ((x < W) && (y < H)) {
             const size_t pix = (size_t)y * W + x;
             last[p] = n_contrib[pix];
             T[p] = __ldg(final_T + pix);
@@ -294,24 +301,28 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     const unsigned *ids = ids_sorted + range.x;
     const unsigned wlast = wmax;                        // warp-level bound
 
-    // step k (0 .. nchunks-1) handles chunk c = nchunks-1-k (back to front) in stage k % kStages
-    if (producer) {
-        if (lane == 0) {
-            for (int k = 0; k < nchunks; k++) {
-                const int c = nchunks - 1 - k, st = k % kStages;
-                if (k >= kStages) mbar_wait(&sm.empty[st], (uint32_t)(((k / kStages) - 1) & 1));
-                const uint32_t bytes = (uint32_t)min(kChunk, n - c * kChunk) * (uint32_t)sizeof(Rec);
-                mbar_expect_tx(&sm.full[st], bytes);
-                tma_bulk_g2s(&sm.rec[st][0], src + (size_t)c * kChunk, bytes, &sm.full[st]);
-            }
-            // every chunk is consumed by the warp that owns the longest list, so all copies have landed before that warp
-            // (and therefore the CTA) can finish; still, wait for the tail explicitly
-            for (int k = max(0, nchunks - kStages); k < nchunks; k++) mbar_wait(&sm.full[k % kStages], (uint32_t)((k / kStages) & 1));
+    // step k (0 .. nchunks-1) handles chunk c = nchunks-1-k (back to front) in stage k % kStages.  Warp 0's lane 0 feeds
+    // the ring: step k itself (blocking if its stage is still in use), then up to kStages - 1 steps ahead (non-blocking).
+    int next_issue = 0;
+    auto issue = [&](int k) {
+        const int c = nchunks - 1 - k, st = k % kStages;
+        const uint32_t bytes = (uint32_t)min(kChunk, n - c * kChunk) * (uint32_t)sizeof(Rec);
+        mbar_expect_tx(&sm.full[st], bytes);
+        tma_bulk_g2s(&sm.rec[st][0], src + (size_t)c * kChunk, bytes, &sm.full[st]);
+    };
+    auto produce = [&](int k) {
+        while (next_issue < nchunks && next_issue <= k) {
+            if (next_issue >= kStages) mbar_wait(&sm.empty[next_issue % kStages], (uint32_t)(((next_issue / kStages) - 1) & 1));
+            issue(next_issue++);
         }
-        return;
-    }
+        while (next_issue < nchunks && next_issue < k + kStages) {
+            if (next_issue >= kStages && !mbar_try_wait(&sm.empty[next_issue % kStages], (uint32_t)(((next_issue / kStages) - 1) & 1))) break;
+            issue(next_issue++);
+        }
+    };
     for (int k = 0; k < nchunks; k++) {
         const int c = nchunks - 1 - k, s = k % kStages;
+        if (warp == 0) { if (lane == 0) produce(k); __syncwarp(); }
         // Every warp observes EVERY phase of the full barrier, also for chunks it does not need: a warp that skipped the
         // wait could come back to this stage while the barrier is still one phase behind and the parity test would alias.
         mbar_wait(&sm.full[s], (uint32_t)((k / kStages) & 1));

@@ -213,3 +213,35 @@ def test_full_size_properties_cfg5_like():
     for k in ga:
         scale = float(gab[k].abs().max())
         assert float((ga[k] + gb[k] - gab[k]).abs().max()) <= 5e-4 * scale, k
+
+
+def _allreduce_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        dev = torch.device("cuda", rank)
+        vsr = multiview.ViewShardedRasterizer(5000, 16, dev)
+        g = torch.Generator(device=dev); g.manual_seed(77 + rank)
+        src = torch.randn(vsr.grads.flat.numel(), device=dev, generator=g)
+        ref = src.clone(); dist.all_reduce(ref)
+        vsr.grads.flat.copy_(src)
+        got = vsr.all_reduce()
+        ok = bool(torch.allclose(got, ref, rtol=1e-6, atol=1e-6))
+        if rank == 0:
+            open(out, "w").write("%s|%s" % (ok, vsr.collective))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_own_nvlink_allreduce_matches_nccl(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "r.txt")
+    mp.spawn(_allreduce_worker, args=(2, port, out), nprocs=2, join=True)
+    ok, how = open(out).read().split("|")
+    assert ok == "True", how

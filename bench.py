@@ -145,6 +145,7 @@ def cam_settings(cam, a, bg):
 def time_cpu_oracle(a, cloud, cams, ups, steps, warmup):
     """The CPU arm: the oracle port (float32, OpenMP over all host threads), one full view fwd+bwd per step."""
     from oracle import c_oracle
+    c_oracle.set_threads(os.cpu_count() or 1)       # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     bg = np.ones(3, np.float32)
     inputs = dict(means3D=cloud["means3D"], opacities=cloud["opacities"], shs=cloud["shs"], scales=cloud["scales"],
                   rotations=cloud["rotations"])

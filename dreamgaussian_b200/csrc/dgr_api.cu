@@ -156,7 +156,7 @@ int sm_count_raw() {
 }
 int sm_count() { return g_snake ? sm_count_raw() : (1 << 30); }      // a huge "SM count" disables the snake order
 // tuning knobs (dgr_set_tuning): pixels per lane of the render kernels, heaviest-first tile order on/off
-int g_ppl_fwd = 1, g_ppl_bwd = 2;
+int g_ppl_fwd = 1, g_ppl_bwd = 2, g_bwd_pair = 1;
 bool g_no_order = false;
 bool g_emit_attr_set = false;
 }  // namespace
@@ -192,7 +192,8 @@ int dgr_profile_collect(char *names, size_t names_bytes, float *ms, int max) {
 
 int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order) {
     if ((ppl_fwd != 1 && ppl_fwd != 2 && ppl_fwd != 4) || (ppl_bwd != 1 && ppl_bwd != 2 && ppl_bwd != 4)) return fail(-1, "ppl must be 1, 2 or 4");
-    g_ppl_fwd = ppl_fwd; g_ppl_bwd = ppl_bwd; g_no_order = tile_order == 0; g_snake = tile_order != 2;
+    g_ppl_fwd = ppl_fwd; g_ppl_bwd = ppl_bwd; g_bwd_pair = (tile_order & 4) == 0; tile_order &= 3;
+    g_no_order = tile_order == 0; g_snake = tile_order != 2;
     return 0;
 }
 
@@ -321,14 +322,15 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
     DGR_CUDA(cudaMemsetAsync(grad_rec, 0, (size_t)g->P * kGradRecFloats * 4, st));
     if (binning && capacity > 0) {
         const unsigned *tile_order = g_no_order ? nullptr : reinterpret_cast<const unsigned *>(image + IL.off_order);
-#define DGR_RENDER_BWD(PPL_)                                                                                              \
+#define DGR_RENDER_BWD(PPL_, U2_)                                                                                              \
     DGR_KERNEL("render_bwd", st, s->debug,                                                                                 \
-               render_bwd_kernel<PPL_><<<(unsigned)tiles, SubTile<PPL_>::kThreads, 0, st>>>(                                   \
+               render_bwd_kernel<PPL_, U2_><<<(unsigned)tiles, SubTile<PPL_>::kThreads, 0, st>>>(                                   \
                    H, W, IL.gx, tile_order, reinterpret_cast<const uint2 *>(image + IL.off_ranges),                        \
                    reinterpret_cast<const Rec *>(binning + BL.off_rec), reinterpret_cast<const unsigned *>(binning + BL.off_ids), \
                    s->bg, reinterpret_cast<const float *>(image + IL.off_finalT),                                          \
                    reinterpret_cast<const unsigned *>(image + IL.off_ncontrib), gin->dL_dcolor, gin->dL_ddepth, gin->dL_dalpha, grad_rec))
-        if (g_ppl_bwd == 4) DGR_RENDER_BWD(4); else if (g_ppl_bwd == 2) DGR_RENDER_BWD(2); else DGR_RENDER_BWD(1);
+        if (g_bwd_pair) { if (g_ppl_bwd == 4) DGR_RENDER_BWD(4, true); else if (g_ppl_bwd == 2) DGR_RENDER_BWD(2, true); else DGR_RENDER_BWD(1, true); }
+        else { if (g_ppl_bwd == 4) DGR_RENDER_BWD(4, false); else if (g_ppl_bwd == 2) DGR_RENDER_BWD(2, false); else DGR_RENDER_BWD(1, false); }
 #undef DGR_RENDER_BWD
     }
     DGR_KERNEL("preprocess_bwd", st, s->debug, DGR_DISPATCH(launch_pre_bwd, s, g, radii, reinterpret_cast<const unsigned *>(geom + GL.off_touched), grad_rec, gout, st));

@@ -243,7 +243,39 @@ __device__ __forceinline__ float reduce12(const float (&v)[12], int lane) {
     return d;
 }
 
-template <int PPL>
+// two independent 12-value reductions with their shuffles interleaved (twice the shuffles in flight per dependent round)
+__device__ __forceinline__ void reduce12x2(const float (&v)[12], const float (&w)[12], int lane, float &rv, float &rw) {
+    float a[6], b[3], e[6], f[3];
+    bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const float keep = hi ? v[i + 6] : v[i], send = hi ? v[i] : v[i + 6];
+        const float keep2 = hi ? w[i + 6] : w[i], send2 = hi ? w[i] : w[i + 6];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        e[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 16);
+    }
+    hi = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float keep = hi ? a[i + 3] : a[i], send = hi ? a[i] : a[i + 3];
+        const float keep2 = hi ? e[i + 3] : e[i], send2 = hi ? e[i] : e[i + 3];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        f[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 8);
+    }
+    hi = (lane & 4) != 0;
+    const float c0 = (hi ? b[2] : b[0]) + __shfl_xor_sync(0xffffffffu, hi ? b[0] : b[2], 4);
+    const float g0 = (hi ? f[2] : f[0]) + __shfl_xor_sync(0xffffffffu, hi ? f[0] : f[2], 4);
+    const float c1 = (hi ? 0.f : b[1]) + __shfl_xor_sync(0xffffffffu, hi ? b[1] : 0.f, 4);
+    const float g1 = (hi ? 0.f : f[1]) + __shfl_xor_sync(0xffffffffu, hi ? f[1] : 0.f, 4);
+    hi = (lane & 2) != 0;
+    float d = (hi ? c1 : c0) + __shfl_xor_sync(0xffffffffu, hi ? c0 : c1, 2);
+    float h = (hi ? g1 : g0) + __shfl_xor_sync(0xffffffffu, hi ? g0 : g1, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    h += __shfl_xor_sync(0xffffffffu, h, 1);
+    rv = d; rw = h;
+}
+
+template <int PPL, bool U2>
 __global__ void __launch_bounds__(SubTile<PPL>::kThreads)
 render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const uint2 *__restrict__ ranges,
                   const Rec *__restrict__ rec_sorted, const unsigned *__restrict__ ids_sorted, const float *__restrict__ bg,
@@ -343,9 +375,9 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
                 my_id = __ldg(ids + (size_t)c * kChunk + i);
             }
             unsigned mask = __ballot_sync(0xffffffffu, hit);
-            while (mask) {
-                const int j = 31 - __clz(mask);
-                mask &= ~(1u << j);
+            // evaluates record b+j for this warp's pixels, advancing T and R; v = this lane's 10 moment contributions;
+            // returns (warp-uniform) whether any lane contributed
+            auto eval = [&](int j, float (&v)[12]) -> bool {
                 const Rec *r = &sm.rec[s][b + j];
                 const float4 q0 = r->q0, q1 = r->q1;
                 const unsigned gidx = (unsigned)(c * kChunk + b + j);
@@ -361,8 +393,7 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
                     okv[p] = (gidx < last[p]) & (p2 <= 0.f) & (av[p] >= DGR_ALPHA_MIN);
                     any_ok = any_ok || okv[p];
                 }
-                if (!__any_sync(0xffffffffu, any_ok)) continue;
-                float v[12];
+                if (!__any_sync(0xffffffffu, any_ok)) return false;
 #pragma unroll
                 for (int q = 0; q < 12; q++) v[q] = 0.f;
                 if (any_ok) {
@@ -385,11 +416,38 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
                         }
                     }
                 }
+                return true;
+            };
+            const int comp = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0) + ((lane >> 1) & 3);
+            const bool writer = ((lane & 1) == 0) && ((lane & 6) != 6) && comp < 10;
+            while (mask) {
+                const int j = 31 - __clz(mask);
+                mask &= ~(1u << j);
+                float v[12];
+                if (!eval(j, v)) continue;
+                if constexpr (U2) {
+                    // pair this record with the next contributing one so that two butterflies overlap
+                    float v2[12];
+                    int j2 = -1;
+                    while (mask) {
+                        const int jj = 31 - __clz(mask);
+                        mask &= ~(1u << jj);
+                        if (eval(jj, v2)) { j2 = jj; break; }
+                    }
+                    if (j2 >= 0) {
+                        float red, red2;
+                        reduce12x2(v, v2, lane, red, red2);
+                        const unsigned gid = __shfl_sync(0xffffffffu, my_id, j), gid2 = __shfl_sync(0xffffffffu, my_id, j2);
+                        if (writer) {
+                            red_add_f32(grad_rec + (size_t)gid * kGradRecFloats + comp, red);
+                            red_add_f32(grad_rec + (size_t)gid2 * kGradRecFloats + comp, red2);
+                        }
+                        continue;
+                    }
+                }
                 const float red = reduce12(v, lane);
                 const unsigned gid = __shfl_sync(0xffffffffu, my_id, j);
-                const int comp = ((lane & 16) ? 6 : 0) + ((lane & 8) ? 3 : 0) + ((lane >> 1) & 3);
-                if (((lane & 1) == 0) && ((lane & 6) != 6) && comp < 10)
-                    red_add_f32(grad_rec + (size_t)gid * kGradRecFloats + comp, red);
+                if (writer) red_add_f32(grad_rec + (size_t)gid * kGradRecFloats + comp, red);
             }
         }
         __syncwarp();

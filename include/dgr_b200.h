@@ -109,7 +109,8 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom, 
                        uint64_t *counts_host, void *count_ready_event, void *stream);
 
 /* Tuning knobs (process-wide; results do not depend on them): pixels per lane of the forward / backward render
- * kernels (1, 2 or 4) and whether tiles are issued heaviest-first (1) or in row-major order (0). */
+ * kernels (1, 2 or 4); tile_order bits 0-1: 0 = row-major tile issue, 1 = heaviest-first with snake order over the SMs,
+ * 2 = heaviest-first plain; bit 2 (value 4) turns OFF the backward kernel's paired warp reductions (A/B switch). */
 int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order);
 
 /* Thin cudaEvent wrappers so a host without the CUDA runtime headers (ctypes, cgo ...) can use the protocol above. */

@@ -211,7 +211,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         d_rot = torch.empty((P, 4), **f32) if rotations is not None else None
         d_cov = torch.empty((P, 6), **f32) if cov3D is not None else None
         backward_impl(state, gC, gD, gA, d_means3D, d_means2D, d_sh, d_col, d_opac, d_scales, d_rot, d_cov)
-        ctx.state = None
+        # ctx.state stays: a retain_graph backward runs again from the same buffers (they go away with the graph node)
         return d_means3D, d_means2D, d_sh, d_col, d_opac, d_scales, d_rot, d_cov, None
 
 

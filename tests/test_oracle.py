@@ -191,6 +191,18 @@ def test_invariants_alpha_culling_permutation():
     assert (refp["radii"] == ref["radii"][perm]).all()
 
 
+def test_padded_sh_storage_is_ignored_beyond_the_active_degree():
+    """gs_renderer.py:806: shs = get_features with (max_sh_degree+1)^2 rows while sh_degree = active_sh_degree."""
+    s, i = h.make_case(P=300, res=48, deg=1, sigma=0.05, elev=15, azim=70)
+    pad = dict(i)
+    pad["shs"] = np.concatenate([i["shs"], np.random.default_rng(3).normal(size=(300, 12, 3)).astype(np.float32)], axis=1)
+    g = h.upstream_grads(48, 48)
+    a, b = h.run_oracle(s, i, g), h.run_oracle(s, pad, g)
+    assert np.array_equal(a["color"], b["color"])
+    assert not b["grads"]["shs"][:, 4:].any()
+    assert np.array_equal(b["grads"]["shs"][:, :4], a["grads"]["shs"])
+
+
 def test_oracle_edge_cases_empty_and_validation():
     cam = scene.orbit_camera(0, 0, 2.0, 32, 24)
     st = _settings(cam, 0, bg=(0.1, 0.2, 0.3))

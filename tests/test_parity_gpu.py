@@ -140,6 +140,45 @@ def test_forward_is_deterministic_and_tuning_independent():
             assert torch.equal(a, b)          # bit-identical: per-pixel arithmetic does not depend on the launch shape
 
 
+def test_padded_sh_storage_with_lower_active_degree():
+    """gs_renderer.py:806 passes get_features ([P, (max_sh_degree+1)^2, 3]) with sh_degree=active_sh_degree: the storage can
+    hold more coefficients than the active degree reads.  Unused coefficients change nothing and get zero gradient."""
+    s, i = h.make_case(P=600, res=72, deg=1, sigma=0.05, elev=15, azim=70)
+    rng = np.random.default_rng(3)
+    padded = dict(i)
+    padded["shs"] = np.concatenate([i["shs"], rng.normal(size=(600, 12, 3)).astype(np.float32)], axis=1)      # M = 16, 4 in use
+    g = h.upstream_grads(72, 72)
+    ref = h.run_oracle(s, padded, g)
+    cu = h.run_cuda(s, padded, g)
+    ok, rep = h.compare(cu, ref)
+    assert ok, rep
+    assert cu["grads"]["shs"].shape == (600, 16, 3)
+    assert not cu["grads"]["shs"][:, 4:].any()
+    small = h.run_cuda(s, i, g)
+    assert np.array_equal(cu["color"], small["color"])
+    assert np.array_equal(cu["grads"]["shs"][:, :4], small["grads"]["shs"]) or \
+        np.abs(cu["grads"]["shs"][:, :4] - small["grads"]["shs"]).max() <= 2e-5 * np.abs(small["grads"]["shs"]).max()
+
+
+def test_backward_twice_of_one_forward_gives_the_same_gradients():
+    """retain_graph: a second backward through the same forward runs from the same geometry / binning / image buffers and
+    must not see the first one's per-Gaussian moment accumulators."""
+    s, i = h.make_case(P=5000, res=160, deg=2)
+    ti, rs = _torch_inputs(i), _settings(s)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in ti.items()}
+    m2d = torch.zeros_like(ti["means3D"], requires_grad=True)
+    img, radii, depth, alpha = R.GaussianRasterizer(rs)(means2D=m2d, **leaves)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    up = torch.randn(img.shape, device="cuda", generator=g)
+    loss = (img * up).sum() + alpha.sum()
+    names = list(leaves)
+    first = torch.autograd.grad(loss, [leaves[k] for k in names] + [m2d], retain_graph=True)
+    second = torch.autograd.grad(loss, [leaves[k] for k in names] + [m2d])
+    for a, b, k in zip(first, second, names + ["means2D"]):
+        scale = float(a.abs().max()) + 1e-20
+        assert float((a - b).abs().max()) <= 2e-5 * scale, k      # float atomics: order differs, values do not
+
+
 def test_capacity_guess_too_small_is_repaired():
     s, i = h.make_case(P=3000, res=128, deg=1, sigma=0.05)
     ti, rs = _torch_inputs(i), _settings(s)

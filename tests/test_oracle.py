@@ -200,7 +200,7 @@ def test_padded_sh_storage_is_ignored_beyond_the_active_degree():
     a, b = h.run_oracle(s, i, g), h.run_oracle(s, pad, g)
     assert np.array_equal(a["color"], b["color"])
     assert not b["grads"]["shs"][:, 4:].any()
-    assert np.array_equal(b["grads"]["shs"][:, :4], a["grads"]["shs"])
+    np.testing.assert_allclose(b["grads"]["shs"][:, :4], a["grads"]["shs"], rtol=0, atol=1e-11)    # OpenMP summation order
 
 
 def test_oracle_edge_cases_empty_and_validation():

@@ -196,7 +196,7 @@ def run_reference(a, rank, world):
 def run_ours(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from dreamgaussian_b200 import _lib, multiview
+    from dreamgaussian_b200 import _lib, hostmem, multiview
     from dreamgaussian_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
 
     if not torch.cuda.is_available():
@@ -288,11 +288,12 @@ def run_ours(a, rank, world, local_rank):
     e2e = None
     if not a.no_e2e:
         names = ("means3D", "shs", "opacities", "scales", "rotations")
-        host = {k: torch.tensor(cloud[k]).pin_memory() for k in names}
+        # pinned buffers on the GPU's own NUMA node (dreamgaussian_b200/hostmem.py): cross-socket H2D runs at ~20 GB/s, local at ~53
+        host = {k: hostmem.pinned_like(torch.tensor(cloud[k]), dev) for k in names}
         RING = 3
         dev_in = [{k: torch.empty_like(host[k], device=dev).requires_grad_(True) for k in names} for _ in range(RING)]
-        grads_host = [{k: torch.empty_like(host[k]).pin_memory() for k in names} for _ in range(RING)]
-        loss_host = [torch.zeros((1,), dtype=torch.float32).pin_memory() for _ in range(RING)]
+        grads_host = [{k: hostmem.pinned_empty(host[k].shape, host[k].dtype, dev) for k in names} for _ in range(RING)]
+        loss_host = [hostmem.pinned_empty((1,), torch.float32, dev) for _ in range(RING)]
         h2d = sum(v.numel() * 4 for v in host.values())
         d2h = h2d + 4
         s_up, s_comp, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -375,6 +376,7 @@ def run_ours(a, rank, world, local_rank):
         e2e = {"value": P * world * e2e_steps / (float(ms_e.item()) * 1e-3), "unit": "splats/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": float(ms_e.item()) / e2e_steps, "steps": e2e_steps,
                "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / e2e_steps,
+               "host_buffers_numa_local": bool(hostmem.gpu_local_cpus(dev)),
                "note": "public API (GaussianRasterizer + autograd); inputs from / gradients + loss to pinned host memory every step; "
                        "upload, compute and download of consecutive steps overlap on 3 streams"}
 

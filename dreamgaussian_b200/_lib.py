@@ -25,6 +25,7 @@ class DgrGaussians(ctypes.Structure):
         ("P", ctypes.c_int32), ("M", ctypes.c_int32),
         ("means3D", c_f32p), ("shs", c_f32p), ("colors_precomp", c_f32p), ("opacities", c_f32p),
         ("scales", c_f32p), ("rotations", c_f32p), ("cov3D_precomp", c_f32p),
+        ("shs_rest", c_f32p), ("activations", ctypes.c_int32),          # raw GaussianModel parameters
     ]
 
 
@@ -41,6 +42,7 @@ class DgrGaussianGrads(ctypes.Structure):
         ("dL_dmeans3D", c_f32p), ("dL_dmeans2D", c_f32p), ("dL_dshs", c_f32p), ("dL_dcolors_precomp", c_f32p),
         ("dL_dopacities", c_f32p), ("dL_dscales", c_f32p), ("dL_drotations", c_f32p), ("dL_dcov3D_precomp", c_f32p),
         ("accumulate", ctypes.c_int32),
+        ("dL_dshs_rest", c_f32p), ("xyz_gradient_accum", c_f32p), ("denom", c_f32p), ("max_radii2D", c_f32p),
     ]
 
 
@@ -109,7 +111,7 @@ def load():
     lib.dgr_profile_enable.argtypes = [ctypes.c_int]
     lib.dgr_profile_collect.restype = ctypes.c_int
     lib.dgr_profile_collect.argtypes = [ctypes.c_char_p, ctypes.c_size_t, vp, ctypes.c_int]
-    if lib.dgr_abi_version() != 1:
+    if lib.dgr_abi_version() != 2:
         raise RuntimeError("libdgr_b200.so ABI version mismatch")
     _lib = lib
     tune = os.environ.get("DGR_TUNING")        # "ppl_fwd,ppl_bwd,tile_order" for experiments

@@ -80,6 +80,11 @@ int check_gaussians(const DgrSettings *s, const DgrGaussians *g) {
         ((g->scales != nullptr || g->rotations != nullptr) && g->cov3D_precomp != nullptr))
         return fail(-2, "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
     if (g->P > 0 && (!g->means3D || !g->opacities)) return fail(-1, "means3D / opacities must not be NULL");
+    if (g->activations) {
+        if (!g->shs || g->cov3D_precomp || !g->scales || !g->rotations)
+            return fail(-2, "activations: raw parameters need features_dc (shs), scaling and rotation; no cov3D_precomp");
+        if (g->M > 1 && !g->shs_rest) return fail(-2, "activations: shs_rest (_features_rest) is NULL but M > 1");
+    }
     if (g->shs) {
         if (!s->campos) return fail(-1, "campos must not be NULL with SHs");
         const int nb = (s->sh_degree + 1) * (s->sh_degree + 1);
@@ -91,39 +96,45 @@ int check_gaussians(const DgrSettings *s, const DgrGaussians *g) {
 
 constexpr size_t kMaxTileSmem = 200 * 1024;      // tile-histogram rows live in shared memory: up to 51200 tiles
 
-template <int DEG, bool HAS_SH, bool HAS_COV>
+template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
 void launch_pre_fwd(const DgrSettings *s, const DgrGaussians *g, int *radii, char *geom, const GeomLayout &L, unsigned *colscan_done,
                     cudaStream_t st) {
     const size_t smem = (size_t)L.tiles * 4;
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV><<<L.nblocks, kPreThreads, smem, st>>>(
+        cudaFuncSetAttribute(preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV, RAW><<<L.nblocks, kPreThreads, smem, st>>>(
         g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
-        s->campos, g->means3D, g->shs, g->colors_precomp, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii,
+        s->campos, g->means3D, g->shs, g->shs_rest, g->colors_precomp, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii,
         reinterpret_cast<Rec *>(geom + L.off_rec), reinterpret_cast<unsigned *>(geom + L.off_touched),
         reinterpret_cast<unsigned *>(geom + L.off_blkhist), L.tiles, L.iters, colscan_done);
 }
 
-template <int DEG, bool HAS_SH, bool HAS_COV>
+template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
 void launch_pre_bwd(const DgrSettings *s, const DgrGaussians *g, const int *radii, const unsigned *touched, const float *grad_rec,
                     const DgrGaussianGrads *o, cudaStream_t st) {
     const int nb = (g->P + kPreThreads - 1) / kPreThreads;
-    preprocess_bwd_kernel<DEG, HAS_SH, HAS_COV><<<nb, kPreThreads, 0, st>>>(
+    preprocess_bwd_kernel<DEG, HAS_SH, HAS_COV, RAW><<<nb, kPreThreads, 0, st>>>(
         g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
-        s->campos, g->means3D, g->shs, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii, touched, grad_rec,
+        s->campos, g->means3D, g->shs, g->shs_rest, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii, touched, grad_rec,
         o->dL_dmeans3D, o->dL_dmeans2D, o->dL_dshs, o->dL_dcolors_precomp, o->dL_dopacities, o->dL_dscales, o->dL_drotations,
-        o->dL_dcov3D_precomp, o->accumulate);
+        o->dL_dcov3D_precomp, o->dL_dshs_rest, o->xyz_gradient_accum, o->denom, o->max_radii2D, o->accumulate);
 }
 
 #define DGR_DISPATCH(FN, ...)                                                                              \
     do {                                                                                                   \
         const bool sh_ = g->shs != nullptr, cov_ = g->cov3D_precomp != nullptr;                            \
-        if (!sh_) { if (cov_) FN<0, false, true>(__VA_ARGS__); else FN<0, false, false>(__VA_ARGS__); }     \
+        if (g->activations) switch (s->sh_degree) {       /* raw parameters: SH + scale/rotation only */     \
+            case 0: FN<0, true, false, true>(__VA_ARGS__); break;                                           \
+            case 1: FN<1, true, false, true>(__VA_ARGS__); break;                                           \
+            case 2: FN<2, true, false, true>(__VA_ARGS__); break;                                           \
+            default: FN<3, true, false, true>(__VA_ARGS__); break;                                          \
+        }                                                                                                  \
+        else if (!sh_) { if (cov_) FN<0, false, true, false>(__VA_ARGS__); else FN<0, false, false, false>(__VA_ARGS__); } \
         else switch (s->sh_degree) {                                                                       \
-            case 0: if (cov_) FN<0, true, true>(__VA_ARGS__); else FN<0, true, false>(__VA_ARGS__); break;  \
-            case 1: if (cov_) FN<1, true, true>(__VA_ARGS__); else FN<1, true, false>(__VA_ARGS__); break;  \
-            case 2: if (cov_) FN<2, true, true>(__VA_ARGS__); else FN<2, true, false>(__VA_ARGS__); break;  \
-            default: if (cov_) FN<3, true, true>(__VA_ARGS__); else FN<3, true, false>(__VA_ARGS__); break; \
+            case 0: if (cov_) FN<0, true, true, false>(__VA_ARGS__); else FN<0, true, false, false>(__VA_ARGS__); break;  \
+            case 1: if (cov_) FN<1, true, true, false>(__VA_ARGS__); else FN<1, true, false, false>(__VA_ARGS__); break;  \
+            case 2: if (cov_) FN<2, true, true, false>(__VA_ARGS__); else FN<2, true, false, false>(__VA_ARGS__); break;  \
+            default: if (cov_) FN<3, true, true, false>(__VA_ARGS__); else FN<3, true, false, false>(__VA_ARGS__); break; \
         }                                                                                                  \
     } while (0)
 

@@ -39,22 +39,23 @@ __device__ __forceinline__ void store_acc(float *p, float v, bool acc) { *p = ac
 // the first 3*NB are bs[k]*gr[ch] and the rest zero); writing them directly would make every store instruction touch
 // 32 different cache lines.  Instead the rows are transposed through shared memory in chunks of 24 floats
 // (row stride 25 words: conflict-free) and written back with consecutive lanes on consecutive addresses.
-template <int DEG>
+// FIRST = 1: the destination rows are GaussianModel._features_rest ([P, M-1, 3], coefficients 1 .. M-1).
+template <int DEG, int FIRST = 0>
 __device__ __forceinline__ void store_sh_grads(float *__restrict__ dL_dshs, int P, int M, const float (&bs)[16],
                                                const float (&gr)[3], bool acc, float *stage /* [32*25] of this warp */) {
-    constexpr int NB = (DEG + 1) * (DEG + 1);
+    constexpr int NB = (DEG + 1) * (DEG + 1) - FIRST;
     const int lane = threadIdx.x & 31;
     const int row_base = (int)(blockIdx.x * blockDim.x) + (int)(threadIdx.x & ~31u);
     const int nrows = min(32, P - row_base);
     if (nrows <= 0) return;
-    const int rowlen = 3 * M;
+    const int rowlen = 3 * (M - FIRST);
 #pragma unroll
     for (int c = 0; c < 2; c++) {
         if (24 * c < rowlen) {
 #pragma unroll
             for (int j = 0; j < 24; j++) {
                 const int f = 24 * c + j;                 // compile-time
-                const float v = (f / 3 < NB) ? bs[(f / 3) < 16 ? (f / 3) : 0] * gr[f % 3] : 0.f;
+                const float v = (f / 3 < NB) ? bs[(f / 3 + FIRST) < 16 ? (f / 3 + FIRST) : 0] * gr[f % 3] : 0.f;
                 if (f < rowlen) stage[lane * 25 + j] = v;
             }
             __syncwarp();
@@ -74,18 +75,20 @@ __device__ __forceinline__ void store_sh_grads(float *__restrict__ dL_dshs, int 
     }
 }
 
-template <int DEG, bool HAS_SH, bool HAS_COV>
+template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
 __global__ void __launch_bounds__(kPreThreads, 4)
 preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, float scale_modifier,
                       const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
                       const float *__restrict__ campos,
-                      const float *__restrict__ means3D, const float *__restrict__ shs,
+                      const float *__restrict__ means3D, const float *__restrict__ shs, const float *__restrict__ shs_rest,
                       const float *__restrict__ opacities, const float *__restrict__ scales,
                       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
                       const int *__restrict__ radii, const unsigned *__restrict__ touched, const float *__restrict__ grad_rec,
                       float *__restrict__ dL_dmeans3D, float *__restrict__ dL_dmeans2D, float *__restrict__ dL_dshs,
                       float *__restrict__ dL_dcolors, float *__restrict__ dL_dopacities, float *__restrict__ dL_dscales,
-                      float *__restrict__ dL_drotations, float *__restrict__ dL_dcov3D, int accumulate) {
+                      float *__restrict__ dL_drotations, float *__restrict__ dL_dcov3D, float *__restrict__ dL_dshs_rest,
+                      float *__restrict__ xyz_gradient_accum, float *__restrict__ denom, float *__restrict__ max_radii2D,
+                      int accumulate) {
     __shared__ FrameConsts fc;
     __shared__ float s_stage[HAS_SH ? (kPreThreads / 32) * 32 * 25 : 1];
     load_frame(fc, viewmatrix, projmatrix, HAS_SH ? campos : nullptr);
@@ -118,13 +121,16 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
         float R[9];
         float3 s = make_float3(0.f, 0.f, 0.f);
         float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+        float inv_qnorm = 1.f;
         if (HAS_COV) {
 #pragma unroll
             for (int i = 0; i < 6; i++) S6[i] = __ldg(cov3D_precomp + 6 * (size_t)g + i);
         } else {
-            s = make_float3(scale_modifier * __ldg(scales + 3 * (size_t)g), scale_modifier * __ldg(scales + 3 * (size_t)g + 1),
-                            scale_modifier * __ldg(scales + 3 * (size_t)g + 2));
+            s = make_float3(__ldg(scales + 3 * (size_t)g), __ldg(scales + 3 * (size_t)g + 1), __ldg(scales + 3 * (size_t)g + 2));
+            if (RAW) s = make_float3(expf(s.x), expf(s.y), expf(s.z));
+            s = make_float3(scale_modifier * s.x, scale_modifier * s.y, scale_modifier * s.z);
             q = ldg_f4(rotations + 4 * (size_t)g);
+            if (RAW) q = act_normalize(q, inv_qnorm);
             quat_to_R(q, R);
             cov3d_from_scale_rot(s, R, S6);
         }
@@ -134,7 +140,7 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
         const float a = geo.cxx, b = geo.cxy, c = geo.cyy;
         const float det = a * c - b * b, di = 1.f / det;
         const float cA = c * di, cB = -b * di, cC = a * di;
-        const float o = __ldg(opacities + g);
+        const float o = RAW ? act_sigmoid(__ldg(opacities + g)) : __ldg(opacities + g);
 
         // pixel-space mean gradient and conic gradient from the moments
         const float gpx = -(cA * m0.y + cB * m0.z), gpy = -(cC * m0.z + cB * m0.y);
@@ -150,6 +156,11 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
             store_acc(dL_dmeans2D + 3 * (size_t)g, gndx, acc); store_acc(dL_dmeans2D + 3 * (size_t)g + 1, gndy, acc);
             if (!acc) dL_dmeans2D[3 * (size_t)g + 2] = 0.f;
         }
+        // densification bookkeeping of the training loop (gs_renderer.py:625-627, main.py:279-281), for visible Gaussians:
+        // xyz_gradient_accum += |d L / d means2D[:, :2]| of THIS render, denom += 1, max_radii2D = max(max_radii2D, radii)
+        if (xyz_gradient_accum) xyz_gradient_accum[g] += sqrtf(gndx * gndx + gndy * gndy);
+        if (denom) denom[g] += 1.f;
+        if (max_radii2D) max_radii2D[g] = fmaxf(max_radii2D[g], (float)radii[g]);
         {
             const float *PM = fc.PM;
             const float mul1 = geo.ndcx * geo.pw, mul2 = geo.ndcy * geo.pw;     // ph.x * pw^2, ph.y * pw^2
@@ -170,18 +181,20 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) gr[ch] = ((flags >> ch) & 1u) ? 0.f : g_rgb[ch];
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-            for_each_sh_coeff<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, [&](int k, float c0, float c1, float c2) {
+            auto dir_grad = [&](int k, float c0, float c1, float c2) {
                 const float dotc = c0 * gr[0] + c1 * gr[1] + c2 * gr[2];
                 float bx, by, bz;
                 sh_dbasis(k, dx, dy, dz, bx, by, bz);
-                ddx += bx * dotc; ddy += by * dotc; ddz += bz * dotc; });
+                ddx += bx * dotc; ddy += by * dotc; ddz += bz * dotc; };
+            if (RAW) { if (DEG > 0) for_each_sh_coeff<DEG, 1>(shs_rest + (size_t)g * (M - 1) * 3, ((M - 1) & 3) == 0, dir_grad); }   // d basis_0 = 0
+            else for_each_sh_coeff<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, dir_grad);
             const float dot = dx * ddx + dy * ddy + dz * ddz;
             dmean[0] += (ddx - dx * dot) * il; dmean[1] += (ddy - dy * dot) * il; dmean[2] += (ddz - dz * dot) * il;
         } else if (dL_dcolors) {
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) store_acc(dL_dcolors + 3 * (size_t)g + ch, g_rgb[ch], acc);
         }
-        if (dL_dopacities) store_acc(dL_dopacities + g, g_op, acc);
+        if (dL_dopacities) store_acc(dL_dopacities + g, RAW ? g_op * o * (1.f - o) : g_op, acc);     // sigmoid'
 
         // (2) conic -> cov2D -> (Sigma, T = J Rwv)
         const float d2 = di * di;
@@ -247,19 +260,33 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                 float v = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3; i++) { v += dM[3 * i + k] * R[3 * i + k]; dR[3 * i + k] = dM[3 * i + k] * sv[k]; }
-                if (dL_dscales) store_acc(dL_dscales + 3 * (size_t)g + k, v * scale_modifier, acc);
+                if (dL_dscales) store_acc(dL_dscales + 3 * (size_t)g + k, RAW ? v * sv[k] : v * scale_modifier, acc);     // exp' = exp
             }
             if (dL_drotations) {
                 const float r = q.x, x = q.y, y = q.z, z = q.w;
                 float *out = dL_drotations + 4 * (size_t)g;
-                store_acc(out, 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]), acc);
-                store_acc(out + 1, 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]), acc);
-                store_acc(out + 2, 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]), acc);
-                store_acc(out + 3, 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]), acc);
+                float dq[4];
+                dq[0] = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
+                dq[1] = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
+                dq[2] = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
+                dq[3] = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
+                if (RAW) {          // q = raw / |raw|:  d raw = (dq - q (q . dq)) / |raw|
+                    const float qd = r * dq[0] + x * dq[1] + y * dq[2] + z * dq[3];
+                    dq[0] = (dq[0] - r * qd) * inv_qnorm; dq[1] = (dq[1] - x * qd) * inv_qnorm;
+                    dq[2] = (dq[2] - y * qd) * inv_qnorm; dq[3] = (dq[3] - z * qd) * inv_qnorm;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) store_acc(out + k, dq[k], acc);
             }
         }
     }
-    if (HAS_SH && dL_dshs) store_sh_grads<DEG>(dL_dshs, P, M, bs, gr, acc, s_stage + (threadIdx.x >> 5) * (32 * 25));
+    if (HAS_SH && RAW) {
+        if (dL_dshs && in_range) {                // _features_dc gradient [P,1,3] (zero for culled Gaussians: bs = gr = 0)
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) store_acc(dL_dshs + 3 * (size_t)g + ch, bs[0] * gr[ch], acc);
+        }
+        if (dL_dshs_rest && M > 1) store_sh_grads<DEG, 1>(dL_dshs_rest, P, M, bs, gr, acc, s_stage + (threadIdx.x >> 5) * (32 * 25));
+    } else if (HAS_SH && dL_dshs) store_sh_grads<DEG>(dL_dshs, P, M, bs, gr, acc, s_stage + (threadIdx.x >> 5) * (32 * 25));
 }
 
 }  // namespace dgr

@@ -67,9 +67,10 @@ __device__ __forceinline__ void sh_basis(float x, float y, float z, float (&b)[1
 // Streams one Gaussian's SH row ([M][3] layout) in chunks of 8 coefficients (6 x 128-bit loads in flight when the row is
 // 16-byte aligned, i.e. M % 4 == 0: the deg-1 and deg-3 tensors; scalar loads otherwise) and hands every coefficient to f.
 // Keeping only one chunk live (instead of all 48 floats) is what keeps the per-Gaussian kernels below 64 registers.
-template <int DEG, class F>
+// FIRST = 1 streams coefficients 1 .. NB-1 from a row that starts at coefficient 1 (GaussianModel._features_rest).
+template <int DEG, int FIRST = 0, class F>
 __device__ __forceinline__ void for_each_sh_coeff(const float *row, bool vec, F f) {
-    constexpr int NB = (DEG + 1) * (DEG + 1);
+    constexpr int NB = (DEG + 1) * (DEG + 1) - FIRST;
 #pragma unroll
     for (int k0 = 0; k0 < NB; k0 += 8) {
         constexpr int dummy = 0; (void)dummy;
@@ -88,8 +89,16 @@ __device__ __forceinline__ void for_each_sh_coeff(const float *row, bool vec, F 
             for (int i = 0; i < 24; i++) if (i < 3 * n) c[i] = __ldg(row + 3 * k0 + i);
         }
 #pragma unroll
-        for (int j = 0; j < 8; j++) if (j < n) f(k0 + j, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
+        for (int j = 0; j < 8; j++) if (j < n) f(k0 + j + FIRST, c[3 * j], c[3 * j + 1], c[3 * j + 2]);
     }
+}
+
+// GaussianModel activations (gs_renderer.py:127-138, :196-216), applied in registers when the caller passes the raw
+// parameters (DgrGaussians.activations): scaling = exp, opacity = sigmoid, rotation = F.normalize (eps 1e-12).
+__device__ __forceinline__ float act_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float4 act_normalize(float4 q, float &inv_norm) {
+    inv_norm = 1.f / fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+    return make_float4(q.x * inv_norm, q.y * inv_norm, q.z * inv_norm, q.w * inv_norm);
 }
 
 // Geometry shared by forward and backward: everything up to cov2D for one Gaussian.
@@ -136,12 +145,12 @@ __device__ __forceinline__ void project_geo(const FrameConsts &fc, const float3 
     g.cyy = g.T1[0] * ST1[0] + g.T1[1] * ST1[1] + g.T1[2] * ST1[2] + DGR_COV2D_LOWPASS;
 }
 
-template <int DEG, bool HAS_SH, bool HAS_COV>
+template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
 __global__ void __launch_bounds__(kPreThreads, 4)
 preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, float scale_modifier,
                       const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
                       const float *__restrict__ campos,
-                      const float *__restrict__ means3D, const float *__restrict__ shs,
+                      const float *__restrict__ means3D, const float *__restrict__ shs, const float *__restrict__ shs_rest,
                       const float *__restrict__ colors_precomp, const float *__restrict__ opacities,
                       const float *__restrict__ scales, const float *__restrict__ rotations,
                       const float *__restrict__ cov3D_precomp,
@@ -170,9 +179,12 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
 #pragma unroll
                 for (int i = 0; i < 6; i++) S6[i] = __ldg(cov3D_precomp + 6 * (size_t)g + i);
             } else {
-                const float3 s = make_float3(scale_modifier * __ldg(scales + 3 * (size_t)g), scale_modifier * __ldg(scales + 3 * (size_t)g + 1),
-                                             scale_modifier * __ldg(scales + 3 * (size_t)g + 2));
-                float R[9]; quat_to_R(ldg_f4(rotations + 4 * (size_t)g), R);
+                float3 s = make_float3(__ldg(scales + 3 * (size_t)g), __ldg(scales + 3 * (size_t)g + 1), __ldg(scales + 3 * (size_t)g + 2));
+                if (RAW) s = make_float3(expf(s.x), expf(s.y), expf(s.z));
+                s = make_float3(scale_modifier * s.x, scale_modifier * s.y, scale_modifier * s.z);
+                float4 q = ldg_f4(rotations + 4 * (size_t)g);
+                if (RAW) { float inv; q = act_normalize(q, inv); }
+                float R[9]; quat_to_R(q, R);
                 cov3d_from_scale_rot(s, R, S6);
             }
             const float fx = (float)W / (2.f * tanfovx), fy = (float)H / (2.f * tanfovy);
@@ -195,7 +207,7 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                 const int rmaxy = min(gy, max(0, (int)((my + rad_f + (kTile - 1)) / kTile)));
                 if (rmaxx > rminx && rmaxy > rminy) {
                     radius_out = (int)rad_f;
-                    const float o = __ldg(opacities + g);
+                    const float o = RAW ? act_sigmoid(__ldg(opacities + g)) : __ldg(opacities + g);
                     // colour
                     float cr, cg, cb;
                     if (HAS_SH) {
@@ -204,6 +216,12 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                         dx *= il; dy *= il; dz *= il;
                         float b[16]; sh_basis<DEG>(dx, dy, dz, b);
                         cr = 0.f; cg = 0.f; cb = 0.f;
+                        if (RAW) {          // _features_dc [P,1,3] + _features_rest [P,M-1,3]: no torch.cat copy
+                            cr = b[0] * __ldg(shs + 3 * (size_t)g); cg = b[0] * __ldg(shs + 3 * (size_t)g + 1); cb = b[0] * __ldg(shs + 3 * (size_t)g + 2);
+                            if (DEG > 0)
+                                for_each_sh_coeff<DEG, 1>(shs_rest + (size_t)g * (M - 1) * 3, ((M - 1) & 3) == 0, [&](int k, float c0, float c1, float c2) {
+                                    cr += b[k] * c0; cg += b[k] * c1; cb += b[k] * c2; });
+                        } else
                         for_each_sh_coeff<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, [&](int k, float c0, float c1, float c2) {
                             cr += b[k] * c0; cg += b[k] * c1; cb += b[k] * c2; });
                         cr += DGR_SH_OFFSET; cg += DGR_SH_OFFSET; cb += DGR_SH_OFFSET;

@@ -59,7 +59,8 @@ def _opt(t, name):
 class _Frame:
     """ctypes views of one forward call's settings + inputs (keeps the tensors alive)."""
 
-    def __init__(self, rs: GaussianRasterizationSettings, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D):
+    def __init__(self, rs: GaussianRasterizationSettings, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D,
+                 sh_rest=None, activations=False):
         self.keep = []
         k = self.keep.append
         self.bg = _dev_f32(rs.bg, "bg"); k(self.bg)
@@ -80,6 +81,16 @@ class _Frame:
             if sh.dim() != 3 or sh.shape[0] != P or sh.shape[2] != 3:
                 raise ValueError("shs must have dimensions (num_points, num_coeffs, 3)")
             M = sh.shape[1]
+        if activations:
+            # raw GaussianModel parameters: sh = _features_dc [P,1,3], sh_rest = _features_rest [P,M-1,3]
+            if sh is None or sh.shape[1] != 1:
+                raise ValueError("features_dc must have dimensions (num_points, 1, 3)")
+            if sh_rest is not None and sh_rest.numel() > 0:
+                if sh_rest.dim() != 3 or sh_rest.shape[0] != P or sh_rest.shape[2] != 3:
+                    raise ValueError("features_rest must have dimensions (num_points, num_coeffs - 1, 3)")
+                M = 1 + sh_rest.shape[1]
+            else:
+                sh_rest = None
         for t, n, w in ((colors_precomp, "colors_precomp", 3), (scales, "scales", 3), (rotations, "rotations", 4), (cov3D, "cov3D_precomp", 6)):
             if t is not None and (t.numel() != P * w):
                 raise ValueError("%s must have dimensions (num_points, %d)" % (n, w))
@@ -87,7 +98,8 @@ class _Frame:
             raise ValueError("opacities must have dimensions (num_points, 1)")
         self.P, self.M = P, M
         self.gaussians = _lib.DgrGaussians(P, M, _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities),
-                                           _ptr(scales), _ptr(rotations), _ptr(cov3D))
+                                           _ptr(scales), _ptr(rotations), _ptr(cov3D), _ptr(sh_rest if activations else None),
+                                           1 if activations else 0)
 
 
 def _stream_ptr(device):
@@ -99,7 +111,7 @@ class ForwardState:
     __slots__ = ("rs", "frame", "num_rendered", "capacity", "geom", "binning", "image", "radii", "alpha", "tensors")
 
 
-def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D):
+def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D, sh_rest=None, activations=False):
     """Runs both forward stages through the C ABI. Inputs are validated CUDA float32 tensors (or None).
     Returns (color, radii, depth, alpha, ForwardState).
 
@@ -109,7 +121,7 @@ def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, 
     lib = _lib.load()
     dev = means3D.device
     with torch.cuda.device(dev):
-        fr = _Frame(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D)
+        fr = _Frame(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D, sh_rest, activations)
         H, W, P = int(rs.image_height), int(rs.image_width), fr.P
         u8 = dict(dtype=torch.uint8, device=dev)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
@@ -142,7 +154,7 @@ def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, 
     state = ForwardState()
     state.rs, state.frame, state.num_rendered, state.capacity = rs, fr, n_inst, cap
     state.geom, state.binning, state.image, state.radii, state.alpha = geom, binning, image, radii, alpha
-    state.tensors = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3D)
+    state.tensors = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3D, sh_rest)
     return color, radii, depth, alpha, state
 
 
@@ -165,15 +177,17 @@ def _host_sync_objects(dev):
 
 
 def backward_impl(state, grad_color, grad_depth, grad_alpha, d_means3D, d_means2D, d_sh, d_col, d_opac, d_scales, d_rot,
-                  d_cov, accumulate=False):
-    """Runs the backward through the C ABI, writing (or accumulating) into the given gradient tensors."""
+                  d_cov, accumulate=False, d_sh_rest=None, densify=None):
+    """Runs the backward through the C ABI, writing (or accumulating) into the given gradient tensors.
+    densify = (xyz_gradient_accum, denom, max_radii2D) float32 [P] tensors (any may be None) updated in the same kernel."""
     lib = _lib.load()
     fr = state.frame
     dev = state.radii.device
     with torch.cuda.device(dev):
         gin = _lib.DgrImageGrads(_ptr(grad_color), _ptr(grad_depth), _ptr(grad_alpha))
         gout = _lib.DgrGaussianGrads(_ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh), _ptr(d_col), _ptr(d_opac), _ptr(d_scales),
-                                     _ptr(d_rot), _ptr(d_cov), 1 if accumulate else 0)
+                                     _ptr(d_rot), _ptr(d_cov), 1 if accumulate else 0, _ptr(d_sh_rest),
+                                     *((_ptr(t) for t in densify) if densify is not None else (None, None, None)))
         _lib.check(lib.dgr_backward(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(state.geom), _ptr(state.binning),
                                     ctypes.c_uint64(state.capacity), _ptr(state.image), _ptr(state.radii), _ptr(state.alpha),
                                     ctypes.byref(gin), ctypes.byref(gout), _stream_ptr(dev)))
@@ -195,7 +209,7 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
         state = ctx.state
-        means3D, sh, colors_precomp, opacities, scales, rotations, cov3D = state.tensors
+        means3D, sh, colors_precomp, opacities, scales, rotations, cov3D, _ = state.tensors
         dev = means3D.device
         P, M = state.frame.P, state.frame.M
         f32 = dict(dtype=torch.float32, device=dev)

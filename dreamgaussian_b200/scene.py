@@ -123,6 +123,19 @@ def make_cloud(num_pts: int, sh_degree: int = 3, seed: int = 0, radius: float = 
     return dict(means3D=f32(xyz), scales=f32(scales), rotations=f32(rots), opacities=f32(op), shs=f32(shs))
 
 
+def to_raw_parameters(cloud: dict, seed: int = 0) -> dict:
+    """The same cloud as GaussianModel's RAW parameters (gs_renderer.py:140-160, inverse of the activations at :127-138):
+    _xyz, _features_dc [P,1,3], _features_rest [P,M-1,3], _opacity = logit, _scaling = log, _rotation = unit quaternion
+    times a random positive length (F.normalize must undo it)."""
+    rng = np.random.default_rng(seed + 7919)
+    op = np.clip(cloud["opacities"].astype(np.float64), 1e-6, 1 - 1e-6)
+    length = rng.uniform(0.5, 2.0, (cloud["rotations"].shape[0], 1))
+    f32 = lambda a: np.ascontiguousarray(np.asarray(a, np.float64).astype(np.float32))
+    return dict(xyz=f32(cloud["means3D"]), features_dc=f32(cloud["shs"][:, :1]), features_rest=f32(cloud["shs"][:, 1:]),
+                opacity=f32(np.log(op / (1 - op))), scaling=f32(np.log(cloud["scales"].astype(np.float64))),
+                rotation=f32(cloud["rotations"].astype(np.float64) * length))
+
+
 def bench_views(n: int, width: int, height: int, radius: float = 2.0):
     """The fixed benchmark camera set of SURVEY.md §8(d): orbit(0, 0) then 45-degree azimuth steps."""
     return [orbit_camera(0.0, (45.0 * i) % 360.0 - (360.0 if (45.0 * i) % 360.0 >= 180.0 else 0.0), radius, width, height)

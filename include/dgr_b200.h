@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DGR_ABI_VERSION 1
+#define DGR_ABI_VERSION 2
 
 /* == GaussianRasterizationSettings, the 12-field NamedTuple built at gs_renderer.py:745-758 == */
 typedef struct DgrSettings {
@@ -51,6 +51,13 @@ typedef struct DgrGaussians {
     const float *scales;         /* [P,3]   or NULL (then cov3D_precomp) */
     const float *rotations;      /* [P,4]   (w,x,y,z), consumed un-normalised */
     const float *cov3D_precomp;  /* [P,6]   xx,xy,xz,yy,yz,zz or NULL */
+    /* SURVEY.md §8 row f1 — GaussianModel's RAW parameters with the activations fused into the kernels
+     * (gs_renderer.py:196-216): when activations != 0, `opacities` is _opacity (sigmoid applied here), `scales` is _scaling
+     * (exp), `rotations` is _rotation (F.normalize, eps 1e-12), `shs` is _features_dc [P,1,3] and `shs_rest` is
+     * _features_rest [P,M-1,3] (NULL when M == 1) — no torch.cat copy; M stays the TOTAL coefficient count.  Requires
+     * shs != NULL and cov3D_precomp == NULL.  The gradients come back with respect to the raw tensors. */
+    const float *shs_rest;
+    int32_t activations;
 } DgrGaussians;
 
 /* == outputs of the forward (gs_renderer.py:800) == */
@@ -79,6 +86,13 @@ typedef struct DgrGaussianGrads {
     float *dL_drotations;      /* [P,4]   */
     float *dL_dcov3D_precomp;  /* [P,6]   */
     int32_t accumulate;        /* 0: overwrite; 1: add into the buffers (several views -> one flat gradient) */
+    float *dL_dshs_rest;       /* [P,M-1,3] with DgrGaussians.activations (then dL_dshs is [P,1,3]); else unused */
+    /* Densification bookkeeping fused into the per-Gaussian backward (gs_renderer.py:625-627, main.py:279-281); each may
+     * be NULL.  For every Gaussian with radii > 0 in this render: xyz_gradient_accum += |dL/dmeans2D[:, :2]| (this
+     * render's gradient), denom += 1, max_radii2D = max(max_radii2D, radii).  All float32 [P] (the reference's [P,1]). */
+    float *xyz_gradient_accum;
+    float *denom;
+    float *max_radii2D;
 } DgrGaussianGrads;
 
 /* Scratch sizes.  The caller owns the three scratch buffers (upstream: geomBuffer / binningBuffer / imgBuffer),

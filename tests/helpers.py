@@ -91,6 +91,52 @@ def run_cuda(settings, inputs, grads=None, device="cuda"):
     return out
 
 
+RAW_KEYS = ("xyz", "features_dc", "features_rest", "opacity", "scaling", "rotation")
+
+
+def run_oracle_raw(settings, raw, grads):
+    """Oracle for the fused-activation path: the reference's activations (gs_renderer.py:127-138,196-216)
+    in float64 torch, the rasterizer oracle on the activated values, and the activations' chain rule by autograd."""
+    import torch
+    t = {k: torch.tensor(np.asarray(raw[k], np.float64), requires_grad=True) for k in RAW_KEYS}
+    act = dict(means3D=t["xyz"] * 1.0, shs=torch.cat((t["features_dc"], t["features_rest"]), dim=1),
+               opacities=torch.sigmoid(t["opacity"]), scales=torch.exp(t["scaling"]),
+               rotations=torch.nn.functional.normalize(t["rotation"]))
+    ref = run_oracle(settings, {k: v.detach().numpy() for k, v in act.items()}, grads)
+    keys = list(act)
+    torch.autograd.backward([act[k] for k in keys], [torch.tensor(np.asarray(ref["grads"][k], np.float64)).reshape(act[k].shape) for k in keys])
+    g = {k: t[k].grad.numpy() for k in RAW_KEYS}
+    g["means2D"] = ref["grads"]["means2D"]
+    ref["grads"] = g
+    return ref
+
+
+def run_cuda_raw(settings, raw, grads, stats=None, device="cuda"):
+    """The fused product path: FusedGaussianRasterizer on the raw CUDA tensors."""
+    import torch
+    from dreamgaussian_b200.fused import FusedGaussianRasterizer
+    from dreamgaussian_b200.rasterizer import GaussianRasterizationSettings
+    t = lambda a: torch.tensor(np.asarray(a, np.float32), device=device)
+    rs = GaussianRasterizationSettings(
+        image_height=settings["image_height"], image_width=settings["image_width"], tanfovx=settings["tanfovx"],
+        tanfovy=settings["tanfovy"], bg=t(settings["bg"]), scale_modifier=settings["scale_modifier"],
+        viewmatrix=t(settings["viewmatrix"]), projmatrix=t(settings["projmatrix"]), sh_degree=settings["sh_degree"],
+        campos=t(settings["campos"]), prefiltered=False, debug=False)
+    tin = {k: t(raw[k]).requires_grad_(True) for k in RAW_KEYS}
+    means2D = torch.zeros_like(tin["xyz"], requires_grad=True)
+    color, radii, depth, alpha = FusedGaussianRasterizer(rs)(tin["xyz"], tin["features_dc"], tin["features_rest"], tin["opacity"],
+                                                             tin["scaling"], tin["rotation"], means2D=means2D, stats=stats)
+    gC, gD, gA = grads
+    loss = (color * t(gC)).sum() + (alpha * t(gA)).sum()
+    if gD is not None:
+        loss = loss + (depth * t(gD)).sum()
+    loss.backward()
+    g = {k: (v.grad.detach().cpu().numpy() if v.grad is not None else np.zeros(v.shape, np.float32)) for k, v in tin.items()}
+    g["means2D"] = means2D.grad.detach().cpu().numpy()
+    return dict(color=color.detach().cpu().numpy(), depth=depth.detach().cpu().numpy(), alpha=alpha.detach().cpu().numpy(),
+                radii=radii.cpu().numpy(), grads=g)
+
+
 def compare(cu, ref, check_grads=True):
     """Returns (ok, report dict). cu = CUDA outputs (float32), ref = oracle outputs with flags."""
     rep = {}
@@ -122,7 +168,7 @@ def compare(cu, ref, check_grads=True):
         # against the scale of the other gradients, not against its own round-off
         floor = 1e-3 * max(float(np.abs(v).max()) if v.size else 0.0 for v in ref["grads"].values())
         for k, gr in ref["grads"].items():
-            if k not in cu["grads"]:
+            if k not in cu["grads"] or gr.size == 0:          # e.g. _features_rest of a degree-0 model: [P,0,3]
                 continue
             gc = cu["grads"][k].astype(np.float64).reshape(gr.shape)
             scale = max(float(np.abs(gr).max()) if gr.size else 0.0, floor) or 1.0

@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libdgr_b200.so does not export %s" % name
     assert set(_lib.EXPORTS) <= set(declared)
-    assert lib.dgr_abi_version() == 1
+    assert lib.dgr_abi_version() == 2
 
 
 def test_scratch_size_queries_need_no_gpu():

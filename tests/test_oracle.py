@@ -203,6 +203,28 @@ def test_padded_sh_storage_is_ignored_beyond_the_active_degree():
     np.testing.assert_allclose(b["grads"]["shs"][:, :4], a["grads"]["shs"], rtol=0, atol=1e-11)    # OpenMP summation order
 
 
+def test_raw_parameter_oracle_is_the_activation_chain_rule_of_the_plain_one():
+    """helpers.run_oracle_raw (checker of the fused-activation path) against closed forms of the
+    activations' derivatives (gs_renderer.py:127-138): exp' = exp, sigmoid' = s(1-s), normalize' = (I - q q^T)/|raw|."""
+    s, i = h.make_case(P=200, res=40, deg=2, sigma=0.06, elev=-5, azim=33)
+    raw = scene.to_raw_parameters(i)
+    g = h.upstream_grads(40, 40)
+    plain, fused = h.run_oracle(s, i, g), h.run_oracle_raw(s, raw, g)
+    np.testing.assert_allclose(fused["color"], plain["color"], atol=2e-6)          # float32 round trip of log / logit
+    gp, gf = plain["grads"], fused["grads"]
+    sc, op = np.exp(raw["scaling"].astype(np.float64)), 1 / (1 + np.exp(-raw["opacity"].astype(np.float64)))
+    rtol = 2e-4                                                                    # plain oracle ran on the float32 activated values
+    np.testing.assert_allclose(gf["scaling"], gp["scales"] * sc, rtol=rtol, atol=1e-6 * np.abs(gp["scales"]).max())
+    np.testing.assert_allclose(gf["opacity"], gp["opacities"] * op * (1 - op), rtol=rtol, atol=1e-6 * np.abs(gp["opacities"]).max())
+    np.testing.assert_allclose(gf["features_dc"], gp["shs"][:, :1], rtol=rtol, atol=1e-6)
+    np.testing.assert_allclose(gf["features_rest"], gp["shs"][:, 1:], rtol=rtol, atol=1e-6)
+    r = raw["rotation"].astype(np.float64)
+    n = np.linalg.norm(r, axis=1, keepdims=True)
+    q = r / n
+    want = (gp["rotations"] - q * (q * gp["rotations"]).sum(1, keepdims=True)) / n
+    np.testing.assert_allclose(gf["rotation"], want, rtol=rtol, atol=2e-6 * np.abs(want).max())
+
+
 def test_oracle_edge_cases_empty_and_validation():
     cam = scene.orbit_camera(0, 0, 2.0, 32, 24)
     st = _settings(cam, 0, bg=(0.1, 0.2, 0.3))

@@ -160,6 +160,66 @@ def test_padded_sh_storage_with_lower_active_degree():
         np.abs(cu["grads"]["shs"][:, :4] - small["grads"]["shs"]).max() <= 2e-5 * np.abs(small["grads"]["shs"]).max()
 
 
+RAW_CASES = {
+    "raw_deg0": dict(P=300, res=64, deg=0, sigma=0.06, elev=5, azim=20),                 # _features_rest is [P,0,3]
+    "raw_deg1": dict(P=400, res=64, deg=1, sigma=0.05, elev=-10, azim=120),
+    "raw_deg2_scale_modifier": dict(P=500, res=80, deg=2, sigma=0.05, elev=25, azim=-100, scale_modifier=1.4),
+    "raw_deg3_20k_400": dict(P=20000, res=400, deg=3),
+}
+
+
+@pytest.mark.parametrize("name", list(RAW_CASES))
+def test_fused_activation_path_parity(name):
+    """raw GaussianModel parameters in, activations + their chain rule inside the kernels."""
+    s, i = h.make_case(**RAW_CASES[name])
+    raw = scene.to_raw_parameters(i)
+    g = h.upstream_grads(s["image_height"], s["image_width"])
+    ok, rep = h.compare(h.run_cuda_raw(s, raw, g), h.run_oracle_raw(s, raw, g))
+    assert ok, rep
+
+
+def test_fused_path_matches_torch_activations_plus_plain_op_and_updates_densify_stats():
+    from dreamgaussian_b200.fused import DensifyStats, FusedGaussianRasterizer
+    s, i = h.make_case(P=3000, res=128, deg=3, sigma=0.03)
+    raw = {k: torch.tensor(v, device="cuda") for k, v in scene.to_raw_parameters(i).items()}
+    rs = _settings(s)
+    # reference formulation (gs_renderer.py:196-216, 762-806): torch activations + cat, then the plain op
+    lv = {k: v.clone().requires_grad_(True) for k, v in raw.items()}
+    m2d = torch.zeros_like(lv["xyz"], requires_grad=True)
+    img, radii, depth, alpha = R.GaussianRasterizer(rs)(
+        means3D=lv["xyz"], means2D=m2d, shs=torch.cat((lv["features_dc"], lv["features_rest"]), dim=1),
+        opacities=torch.sigmoid(lv["opacity"]), scales=torch.exp(lv["scaling"]), rotations=torch.nn.functional.normalize(lv["rotation"]))
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    up, upa = torch.randn(img.shape, device="cuda", generator=gen), torch.randn(alpha.shape, device="cuda", generator=gen)
+    ((img * up).sum() + (alpha * upa).sum()).backward()
+    # fused
+    lf = {k: v.clone().requires_grad_(True) for k, v in raw.items()}
+    m2f = torch.zeros_like(lf["xyz"], requires_grad=True)
+    stats = DensifyStats(3000, "cuda")
+    stats.max_radii2D.fill_(3.0)
+    out = FusedGaussianRasterizer(rs)(lf["xyz"], lf["features_dc"], lf["features_rest"], lf["opacity"], lf["scaling"], lf["rotation"],
+                                      means2D=m2f, stats=stats)
+    ((out[0] * up).sum() + (out[3] * upa).sum()).backward()
+    assert torch.equal(out[1], radii)
+    assert float((out[0] - img).abs().max()) <= 2e-5 and float((out[3] - alpha).abs().max()) <= 2e-5
+    for k in lv:
+        a, b = lf[k].grad, lv[k].grad
+        assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max()) + 1e-12, k
+    vis = radii > 0
+    norm = m2f.grad[:, :2].norm(dim=-1)
+    assert torch.allclose(stats.xyz_gradient_accum[vis], norm[vis], rtol=1e-5, atol=1e-12) and not stats.xyz_gradient_accum[~vis].any()
+    assert torch.equal(stats.denom, vis.float())
+    want = torch.where(vis, torch.maximum(torch.full_like(stats.max_radii2D, 3.0), radii.float()), torch.full_like(stats.max_radii2D, 3.0))
+    assert torch.equal(stats.max_radii2D, want)
+    # a second render accumulates
+    lf2 = {k: v.clone().requires_grad_(True) for k, v in raw.items()}
+    out2 = FusedGaussianRasterizer(rs)(lf2["xyz"], lf2["features_dc"], lf2["features_rest"], lf2["opacity"], lf2["scaling"], lf2["rotation"],
+                                       stats=stats)
+    ((out2[0] * up).sum() + (out2[3] * upa).sum()).backward()
+    assert torch.equal(stats.denom, 2 * vis.float())
+    assert torch.allclose(stats.xyz_gradient_accum[vis], 2 * norm[vis], rtol=1e-4, atol=1e-12)
+
+
 def test_backward_twice_of_one_forward_gives_the_same_gradients():
     """retain_graph: a second backward through the same forward runs from the same geometry / binning / image buffers and
     must not see the first one's per-Gaussian moment accumulators."""

@@ -402,6 +402,15 @@ def run_ours(a, rank, world, local_rank):
                               "achieved": algorithmic_bytes(P, M, H, W, n_inst) / (ms_per_step * 1e-3) / 1e9,
                               "frac": algorithmic_bytes(P, M, H, W, n_inst) / (ms_per_step * 1e-3) / 1e9 / peak},
                      "note": "render kernels are issue/MUFU-bound, not HBM-bound (DESIGN.md); fractions are against the HBM copy peak"})
+    if dom:
+        # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of this same workload
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+            if tr.get("workload") == workload_name(a) and dom in tr["bytes_per_launch"]:
+                roof["traffic"] = tr["bytes_per_launch"][dom]
+                roof["traffic_source"] = tr["source"]
+        except Exception:
+            pass
     out = {
         "metric": "splats/sec fwd+bwd @ %dx%d" % (H, W), "value": value, "unit": "splats/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -12,6 +12,7 @@
 #include "dgr_backward.cuh"
 #include "dgr_binning.cuh"
 #include "dgr_collective.cuh"
+#include "dgr_knn.cuh"
 #include "dgr_common.cuh"
 #include "dgr_preprocess.cuh"
 #include "dgr_render.cuh"
@@ -367,6 +368,39 @@ int dgr_peer_allreduce(const uint64_t *peer_ptrs, int32_t world, int32_t rank, u
         for (int w = 0; w < kMaxPeers; w++) pp.p[w] = w < world ? reinterpret_cast<float *>(peer_ptrs[w]) : nullptr;
         DGR_KERNEL("allreduce_p2p", st, 0, allreduce_p2p_kernel<<<grid, 512, 0, st>>>(pp, world, rank, n4));
     }
+    return 0;
+}
+
+size_t dgr_knn_scratch_bytes(int32_t P) { return KnnLayout(P).total; }
+
+int dgr_dist_cuda2(int32_t P, const float *points, float *mean_dists, void *scratch_v, void *stream) {
+    if (P < 0) return fail(-1, "P < 0");
+    if (P == 0) return 0;
+    if (!points || !mean_dists || !scratch_v) return fail(-1, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *scratch = (char *)scratch_v;
+    KnnLayout L(P);
+    KnnGrid *grid = reinterpret_cast<KnnGrid *>(scratch + L.off_grid);
+    unsigned *cell_start = reinterpret_cast<unsigned *>(scratch + L.off_start);
+    unsigned *cell_fill = reinterpret_cast<unsigned *>(scratch + L.off_fill);
+    unsigned *sums = reinterpret_cast<unsigned *>(scratch + L.off_sums);
+    unsigned *cid = reinterpret_cast<unsigned *>(scratch + L.off_cid);
+    float4 *sorted = reinterpret_cast<float4 *>(scratch + L.off_sorted);
+    DGR_CUDA(cudaMemsetAsync(grid, 0, sizeof(KnnGrid), st));
+    DGR_CUDA(cudaMemsetAsync(grid, 0xff, 3 * sizeof(unsigned), st));                      // lo[] = +inf in the ordered encoding
+    DGR_CUDA(cudaMemsetAsync(cell_start, 0, (L.cap + 1) * 4, st));
+    DGR_CUDA(cudaMemsetAsync(cell_fill, 0, L.cap * 4, st));
+    const int nb = (P + 255) / 256;
+    const int nb_bbox = nb < 4 * sm_count_raw() ? nb : 4 * sm_count_raw();
+    const size_t n_scan = L.cap + 1;
+    DGR_KERNEL("knn_bbox", st, 0, knn_bbox_kernel<<<nb_bbox, 256, 0, st>>>(P, points, grid));
+    DGR_KERNEL("knn_grid", st, 0, knn_grid_kernel<<<1, 1, 0, st>>>(P, (unsigned)L.cap, grid));
+    DGR_KERNEL("knn_count", st, 0, knn_count_kernel<<<nb, 256, 0, st>>>(P, points, grid, cell_start, cid));
+    DGR_KERNEL("knn_scan_sums", st, 0, knn_scan_sums_kernel<<<(unsigned)L.nblk, 1024, 0, st>>>(cell_start, n_scan, sums));
+    DGR_KERNEL("knn_scan_top", st, 0, knn_scan_top_kernel<<<1, 1024, 0, st>>>(sums, L.nblk));
+    DGR_KERNEL("knn_scan_apply", st, 0, knn_scan_apply_kernel<<<(unsigned)L.nblk, 1024, 0, st>>>(cell_start, n_scan, sums));
+    DGR_KERNEL("knn_scatter", st, 0, knn_scatter_kernel<<<nb, 256, 0, st>>>(P, points, cid, cell_start, cell_fill, sorted));
+    DGR_KERNEL("knn_query", st, 0, knn_query_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, grid, cell_start, sorted, mean_dists));
     return 0;
 }
 

@@ -148,6 +148,13 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom, const 
 int dgr_peer_allreduce(const uint64_t *peer_ptrs, int32_t world, int32_t rank, uint64_t n_floats, uint64_t multicast_ptr,
                        void *stream);
 
+/* SURVEY.md §8 row f3 — replaces simple_knn._C.distCUDA2 (/root/reference/simple-knn/spatial.cu:15-26 -> SimpleKNN::knn,
+ * simple_knn.cu:185-221; caller gs_renderer.py:341): mean_dists[i] = mean of the squared distances from point i to its 3
+ * nearest OTHER points (exact; a point set smaller than 4 yields the reference's FLT_MAX arithmetic).  points [P,3] float32.
+ * scratch: dgr_knn_scratch_bytes(P) bytes of device memory.  Stream-ordered, no host synchronisation, no library sort. */
+size_t dgr_knn_scratch_bytes(int32_t P);
+int dgr_dist_cuda2(int32_t P, const float *points, float *mean_dists, void *scratch, void *stream);
+
 /* GaussianRasterizer.markVisible: present[i] = 1 if Gaussian i passes the near-plane test. */
 int dgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
                      uint8_t *present, void *stream);

@@ -50,7 +50,7 @@ EXPORTS = (
     "dgr_abi_version", "dgr_last_error", "dgr_launch_count", "dgr_reset_launch_count",
     "dgr_geom_bytes", "dgr_image_bytes", "dgr_binning_bytes",
     "dgr_forward_preprocess", "dgr_forward_render", "dgr_backward", "dgr_mark_visible", "dgr_debug_geom",
-    "dgr_profile_enable", "dgr_profile_collect", "dgr_event_create", "dgr_event_synchronize", "dgr_event_destroy", "dgr_set_tuning", "dgr_peer_allreduce", "dgr_knn_scratch_bytes", "dgr_dist_cuda2",
+    "dgr_profile_enable", "dgr_profile_collect", "dgr_event_create", "dgr_event_synchronize", "dgr_event_destroy", "dgr_set_tuning", "dgr_peer_allreduce", "dgr_knn_scratch_bytes", "dgr_dist_cuda2", "dgr_fields_scratch_bytes", "dgr_extract_fields",
 )
 
 _lib = None
@@ -107,6 +107,10 @@ def load():
     lib.dgr_knn_scratch_bytes.argtypes = [i32]
     lib.dgr_dist_cuda2.restype = ctypes.c_int
     lib.dgr_dist_cuda2.argtypes = [i32, vp, vp, vp, vp]
+    lib.dgr_fields_scratch_bytes.restype = ctypes.c_size_t
+    lib.dgr_fields_scratch_bytes.argtypes = [i32, i32]
+    lib.dgr_extract_fields.restype = ctypes.c_int
+    lib.dgr_extract_fields.argtypes = [i32, vp, vp, vp, vp, i32, i32, ctypes.c_float, vp, vp, vp, vp]
     lib.dgr_mark_visible.restype = ctypes.c_int
     lib.dgr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
     lib.dgr_debug_geom.restype = ctypes.c_int

@@ -13,6 +13,7 @@
 #include "dgr_binning.cuh"
 #include "dgr_collective.cuh"
 #include "dgr_knn.cuh"
+#include "dgr_fields.cuh"
 #include "dgr_common.cuh"
 #include "dgr_preprocess.cuh"
 #include "dgr_render.cuh"
@@ -401,6 +402,50 @@ int dgr_dist_cuda2(int32_t P, const float *points, float *mean_dists, void *scra
     DGR_KERNEL("knn_scan_apply", st, 0, knn_scan_apply_kernel<<<(unsigned)L.nblk, 1024, 0, st>>>(cell_start, n_scan, sums));
     DGR_KERNEL("knn_scatter", st, 0, knn_scatter_kernel<<<nb, 256, 0, st>>>(P, points, cid, cell_start, cell_fill, sorted));
     DGR_KERNEL("knn_query", st, 0, knn_query_kernel<<<(P + 127) / 128, 128, 0, st>>>(P, grid, cell_start, sorted, mean_dists));
+    return 0;
+}
+
+size_t dgr_fields_scratch_bytes(int32_t P, int32_t num_blocks) { return FieldsLayout(P, num_blocks > 0 ? num_blocks : 1).total; }
+
+int dgr_extract_fields(int32_t P, const float *xyz, const float *opacity_raw, const float *scaling_raw, const float *rotation_raw,
+                       int32_t resolution, int32_t num_blocks, float relax_ratio, float *occ, float *center_scale, void *scratch_v,
+                       void *stream) {
+    if (P < 0 || resolution < 2 || num_blocks < 1) return fail(-1, "bad P / resolution / num_blocks");
+    if (resolution % num_blocks != 0) return fail(-2, "resolution must be a multiple of num_blocks");
+    if (num_blocks > 64) return fail(-3, "num_blocks above 64 not supported");
+    const int split = resolution / num_blocks;
+    const int V = split * split * split;
+    if (V > 16 * kFieldThreads) return fail(-3, "more than 4096 voxels per block not supported");
+    if (!occ || !scratch_v || (P > 0 && (!xyz || !opacity_raw || !scaling_raw || !rotation_raw))) return fail(-1, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *scratch = (char *)scratch_v;
+    FieldsLayout L(P, num_blocks);
+    FieldsHeader *hdr = reinterpret_cast<FieldsHeader *>(scratch + L.off_hdr);
+    unsigned *cell_start = reinterpret_cast<unsigned *>(scratch + L.off_start);
+    unsigned *cell_fill = reinterpret_cast<unsigned *>(scratch + L.off_fill);
+    unsigned *cid = reinterpret_cast<unsigned *>(scratch + L.off_cid);
+    FieldRec *rec = reinterpret_cast<FieldRec *>(scratch + L.off_rec), *sorted = reinterpret_cast<FieldRec *>(scratch + L.off_sorted);
+    DGR_CUDA(cudaMemsetAsync(hdr, 0, sizeof(FieldsHeader), st));
+    DGR_CUDA(cudaMemsetAsync(hdr, 0xff, 3 * sizeof(unsigned), st));
+    DGR_CUDA(cudaMemsetAsync(cell_start, 0, (L.cells + 1) * 4, st));
+    DGR_CUDA(cudaMemsetAsync(cell_fill, 0, L.cells * 4, st));
+    const int nbk = P > 0 ? (P + 255) / 256 : 1;
+    if (P > 0) {
+        const int nb_bbox = nbk < 4 * sm_count_raw() ? nbk : 4 * sm_count_raw();
+        DGR_KERNEL("fields_bbox", st, 0, fields_bbox_kernel<<<nb_bbox, 256, 0, st>>>(P, xyz, opacity_raw, hdr));
+    }
+    DGR_KERNEL("fields_prep", st, 0, fields_prep_kernel<<<nbk, 256, 0, st>>>(P, xyz, opacity_raw, scaling_raw, rotation_raw, hdr, num_blocks,
+                                                                              rec, cid, cell_start, center_scale));
+    DGR_KERNEL("fields_scan", st, 0, fields_scan_kernel<<<1, 1024, 0, st>>>(cell_start, (int)(L.cells + 1)));
+    if (P > 0)
+        DGR_KERNEL("fields_scatter", st, 0, fields_scatter_kernel<<<nbk, 256, 0, st>>>(P, cid, cell_start, cell_fill, rec, sorted));
+    // reference: vmin -= block_size * relax_ratio with python floats (gs_renderer.py:222,264-265) -> one float32 operand
+    const float grow = (float)((2.0 / (double)num_blocks) * (double)relax_ratio);
+    const unsigned grid = (unsigned)L.cells;
+    const int vpt = (V + kFieldThreads - 1) / kFieldThreads;
+#define DGR_FIELDS(VPT_) DGR_KERNEL("fields_eval", st, 0, fields_eval_kernel<VPT_><<<grid, kFieldThreads, 0, st>>>(resolution, num_blocks, split, grow, cell_start, sorted, occ))
+    if (vpt <= 1) DGR_FIELDS(1); else if (vpt <= 2) DGR_FIELDS(2); else if (vpt <= 4) DGR_FIELDS(4); else if (vpt <= 8) DGR_FIELDS(8); else DGR_FIELDS(16);
+#undef DGR_FIELDS
     return 0;
 }
 

@@ -155,6 +155,17 @@ int dgr_peer_allreduce(const uint64_t *peer_ptrs, int32_t world, int32_t rank, u
 size_t dgr_knn_scratch_bytes(int32_t P);
 int dgr_dist_cuda2(int32_t P, const float *points, float *mean_dists, void *scratch, void *stream);
 
+/* SURVEY.md §8 row f4 — GaussianModel.extract_fields (/root/reference/gs_renderer.py:218-294; gaussian_3d_coeff :64-83):
+ * occ[resolution^3] (x-major, z fastest) = per-voxel sum of opacity * exp(-1/2 d^T Sigma^-1 d) over the Gaussians with
+ * sigmoid(opacity) > 0.005 whose normalised centre lies strictly inside the voxel's block's bounding box grown by
+ * relax_ratio * 2/num_blocks.  Inputs are the RAW model tensors (_xyz [P,3], _opacity [P,1], _scaling [P,3], _rotation
+ * [P,4]); center_scale (device, 4 floats, may be NULL) receives the model's `center` and `scale` (:237-238).
+ * resolution % num_blocks == 0, num_blocks <= 64, (resolution/num_blocks)^3 <= 4096.  Stream-ordered, no host read-back. */
+size_t dgr_fields_scratch_bytes(int32_t P, int32_t num_blocks);
+int dgr_extract_fields(int32_t P, const float *xyz, const float *opacity_raw, const float *scaling_raw, const float *rotation_raw,
+                       int32_t resolution, int32_t num_blocks, float relax_ratio, float *occ, float *center_scale, void *scratch,
+                       void *stream);
+
 /* GaussianRasterizer.markVisible: present[i] = 1 if Gaussian i passes the near-plane test. */
 int dgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
                      uint8_t *present, void *stream);

@@ -29,6 +29,11 @@ class DgrGaussians(ctypes.Structure):
     ]
 
 
+class DgrAdamGroup(ctypes.Structure):
+    _fields_ = [("param", c_f32p), ("grad", c_f32p), ("exp_avg", c_f32p), ("exp_avg_sq", c_f32p), ("n", ctypes.c_uint64),
+                ("lr", ctypes.c_float), ("step", ctypes.c_int32)]
+
+
 class DgrImages(ctypes.Structure):
     _fields_ = [("color", c_f32p), ("depth", c_f32p), ("alpha", c_f32p), ("radii", ctypes.c_void_p)]
 
@@ -50,7 +55,7 @@ EXPORTS = (
     "dgr_abi_version", "dgr_last_error", "dgr_launch_count", "dgr_reset_launch_count",
     "dgr_geom_bytes", "dgr_image_bytes", "dgr_binning_bytes",
     "dgr_forward_preprocess", "dgr_forward_render", "dgr_backward", "dgr_mark_visible", "dgr_debug_geom",
-    "dgr_profile_enable", "dgr_profile_collect", "dgr_event_create", "dgr_event_synchronize", "dgr_event_destroy", "dgr_set_tuning", "dgr_peer_allreduce", "dgr_knn_scratch_bytes", "dgr_dist_cuda2", "dgr_fields_scratch_bytes", "dgr_extract_fields",
+    "dgr_profile_enable", "dgr_profile_collect", "dgr_event_create", "dgr_event_synchronize", "dgr_event_destroy", "dgr_set_tuning", "dgr_peer_allreduce", "dgr_knn_scratch_bytes", "dgr_dist_cuda2", "dgr_fields_scratch_bytes", "dgr_extract_fields", "dgr_adam_step",
 )
 
 _lib = None
@@ -111,6 +116,8 @@ def load():
     lib.dgr_fields_scratch_bytes.argtypes = [i32, i32]
     lib.dgr_extract_fields.restype = ctypes.c_int
     lib.dgr_extract_fields.argtypes = [i32, vp, vp, vp, vp, i32, i32, ctypes.c_float, vp, vp, vp, vp]
+    lib.dgr_adam_step.restype = ctypes.c_int
+    lib.dgr_adam_step.argtypes = [ctypes.POINTER(DgrAdamGroup), i32, ctypes.c_double, ctypes.c_double, ctypes.c_double, vp]
     lib.dgr_mark_visible.restype = ctypes.c_int
     lib.dgr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
     lib.dgr_debug_geom.restype = ctypes.c_int

@@ -14,6 +14,7 @@
 #include "dgr_collective.cuh"
 #include "dgr_knn.cuh"
 #include "dgr_fields.cuh"
+#include "dgr_optim.cuh"
 #include "dgr_common.cuh"
 #include "dgr_preprocess.cuh"
 #include "dgr_render.cuh"
@@ -446,6 +447,32 @@ int dgr_extract_fields(int32_t P, const float *xyz, const float *opacity_raw, co
 #define DGR_FIELDS(VPT_) DGR_KERNEL("fields_eval", st, 0, fields_eval_kernel<VPT_><<<grid, kFieldThreads, 0, st>>>(resolution, num_blocks, split, grow, cell_start, sorted, occ))
     if (vpt <= 1) DGR_FIELDS(1); else if (vpt <= 2) DGR_FIELDS(2); else if (vpt <= 4) DGR_FIELDS(4); else if (vpt <= 8) DGR_FIELDS(8); else DGR_FIELDS(16);
 #undef DGR_FIELDS
+    return 0;
+}
+
+int dgr_adam_step(const DgrAdamGroup *groups, int32_t n_groups, double beta1, double beta2, double eps, void *stream) {
+    if (!groups || n_groups < 1 || n_groups > kAdamMaxGroups) return fail(-1, "dgr_adam_step: 1..8 groups");
+    AdamGroups G;
+    G.n_groups = n_groups;
+    unsigned long long run = 0;
+    for (int k = 0; k < n_groups; k++) {
+        const DgrAdamGroup &g = groups[k];
+        if (g.n > 0 && (!g.param || !g.grad || !g.exp_avg || !g.exp_avg_sq)) return fail(-1, "dgr_adam_step: NULL tensor in a non-empty group");
+        G.param[k] = g.param; G.grad[k] = g.grad; G.m[k] = g.exp_avg; G.v[k] = g.exp_avg_sq; G.n[k] = g.n;
+        if (g.step < 1) return fail(-1, "dgr_adam_step: a tensor's step counts from 1");
+        const double bc1 = 1.0 - pow(beta1, (double)g.step), bc2 = 1.0 - pow(beta2, (double)g.step);
+        G.step_size[k] = (float)((double)g.lr / bc1);
+        G.inv_sqrt_bc2[k] = (float)(1.0 / sqrt(bc2));
+        G.start[k] = run; run += (g.n + 3) / 4;
+    }
+    for (int k = n_groups; k <= kAdamMaxGroups; k++) G.start[k] = run;
+    G.start[n_groups] = run;
+    if (run == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long blocks = (run + 255) / 256;
+    const unsigned long long cap = (unsigned long long)sm_count_raw() * 16;
+    if (blocks > cap) blocks = cap;
+    DGR_KERNEL("adam_multi", st, 0, adam_multi_kernel<<<(unsigned)blocks, 256, 0, st>>>(G, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps));
     return 0;
 }
 

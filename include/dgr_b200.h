@@ -166,6 +166,21 @@ int dgr_extract_fields(int32_t P, const float *xyz, const float *opacity_raw, co
                        int32_t resolution, int32_t num_blocks, float relax_ratio, float *occ, float *center_scale, void *scratch,
                        void *stream);
 
+/* SURVEY.md §8 row f2 — the optimiser step of the stage-1 loop: torch.optim.Adam(lr per group, eps) over the model's six
+ * parameter tensors (/root/reference/gs_renderer.py:361-370, stepped at main.py:274-276) as ONE launch.  bias correction 1 - beta^step per tensor; no weight decay, no amsgrad.  betas / eps are doubles because torch derives 1 - beta and
+ * the bias corrections in double before rounding to float32.  Updates param / exp_avg / exp_avg_sq in place. */
+typedef struct DgrAdamGroup {
+    float *param;
+    const float *grad;
+    float *exp_avg;
+    float *exp_avg_sq;
+    uint64_t n;       /* elements */
+    float lr;
+    int32_t step;     /* this tensor's own step count after the update, from 1 (torch keeps state['step'] per tensor: a tensor
+                       * whose .grad was None in some iteration lags behind) */
+} DgrAdamGroup;
+int dgr_adam_step(const DgrAdamGroup *groups, int32_t n_groups, double beta1, double beta2, double eps, void *stream);
+
 /* GaussianRasterizer.markVisible: present[i] = 1 if Gaussian i passes the near-plane test. */
 int dgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
                      uint8_t *present, void *stream);

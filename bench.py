@@ -142,10 +142,30 @@ def cam_settings(cam, a, bg):
                 campos=cam.camera_center)
 
 
+def host_threads():
+    """Threads for the CPU legs: the physical cores this process may run on.  (One OpenMP thread per LOGICAL CPU made the
+    oracle 10x slower on the 2 x 32-core / 128-thread boxes; a cgroup CPU quota, if any, caps it further.)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+        if phys:
+            n = min(n, phys)
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def time_cpu_oracle(a, cloud, cams, ups, steps, warmup):
     """The CPU arm: the oracle port (float32, OpenMP over all host threads), one full view fwd+bwd per step."""
     from oracle import c_oracle
-    c_oracle.set_threads(os.cpu_count() or 1)       # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
+    c_oracle.set_threads(host_threads())            # torchrun exports OMP_NUM_THREADS=1: use every host core anyway
     bg = np.ones(3, np.float32)
     inputs = dict(means3D=cloud["means3D"], opacities=cloud["opacities"], shs=cloud["shs"], scales=cloud["scales"],
                   rotations=cloud["rotations"])

@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--views", type=int, default=8, help="size of the fixed camera set that steps cycle through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-rows", action="store_true", help="skip the short measurements of the SURVEY §8f rows (f1-f4)")
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
 
@@ -161,6 +162,102 @@ def host_threads():
     except Exception:
         pass
     return max(1, n)
+
+
+def measure_next_rows(dev):
+    """Short, guarded measurements of the rows next to the hot path — reported beside the
+    headline metric, never part of it.  Each entry: this library's time and what it is compared with."""
+    import numpy as np
+    import torch
+    from dreamgaussian_b200 import fields, scene, stage1
+    from dreamgaussian_b200.fused import DensifyStats, FusedGaussianRasterizer
+    from dreamgaussian_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    from simple_knn._C import distCUDA2
+    rows = {}
+
+    def ev_median(fn, n):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        evs = []
+        for i in range(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(i); e1.record(); evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return float(np.median([x.elapsed_time(y) for x, y in evs]))
+
+    try:        # f1: raw-parameter step (fwd + bwd + densification statistics) at the bench shape
+        P, res = 100000, 800
+        cloud = scene.make_cloud(P, 3, seed=0, opacity="trained", anisotropic=True)
+        raw = {k: torch.tensor(v, device=dev).requires_grad_(True) for k, v in scene.to_raw_parameters(cloud).items()}
+        t = lambda x: torch.tensor(np.asarray(x, np.float32), device=dev)
+        cams = scene.bench_views(4, res, res)
+        rs = [GaussianRasterizationSettings(image_height=res, image_width=res, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=t(np.ones(3)),
+              scale_modifier=1.0, viewmatrix=t(c.world_view_transform), projmatrix=t(c.full_proj_transform), sh_degree=3,
+              campos=t(c.camera_center), prefiltered=False, debug=False) for c in cams]
+        rng = np.random.default_rng(17)
+        gC, gA = t(rng.normal(size=(3, res, res))), t(rng.normal(size=(1, res, res)))
+        stats = DensifyStats(P, dev)
+        acc, den, mr = torch.zeros((P, 1), device=dev), torch.zeros((P, 1), device=dev), torch.zeros((P,), device=dev)
+
+        def zero():
+            for v in raw.values():
+                v.grad = None
+
+        def ref_form(i):
+            zero()
+            m2d = torch.zeros_like(raw["xyz"], requires_grad=True)
+            c, r, d, al = GaussianRasterizer(rs[i % 4])(means3D=raw["xyz"], means2D=m2d, shs=torch.cat((raw["features_dc"], raw["features_rest"]), dim=1),
+                                                       opacities=torch.sigmoid(raw["opacity"]), scales=torch.exp(raw["scaling"]),
+                                                       rotations=torch.nn.functional.normalize(raw["rotation"]))
+            torch.autograd.backward([c, al], [gC, gA])
+            with torch.no_grad():
+                vis = r > 0
+                mr[vis] = torch.max(mr[vis], r[vis].float()); acc[vis] += torch.norm(m2d.grad[vis, :2], dim=-1, keepdim=True); den[vis] += 1
+
+        def fused(i):
+            zero()
+            c, r, d, al = FusedGaussianRasterizer(rs[i % 4])(raw["xyz"], raw["features_dc"], raw["features_rest"], raw["opacity"], raw["scaling"],
+                                                            raw["rotation"], stats=stats)
+            torch.autograd.backward([c, al], [gC, gA])
+        rows["f1_raw_parameter_step"] = {"ours_ms": ev_median(fused, 40), "torch_activations_plus_plain_op_ms": ev_median(ref_form, 40),
+                                         "shape": "100k / 800x800 / deg 3, fwd+bwd+densify stats through autograd"}
+        del raw, stats
+    except Exception as e:  # noqa: BLE001
+        rows["f1_raw_parameter_step"] = {"error": repr(e)[:200]}
+    try:        # f2: BASELINE.json configs[3]
+        out = {}
+        for name, fz in (("ours", True), ("reference_formulation", False)):
+            stage1.Stage1Trainer(stage1.Stage1Config(), fused=fz).train(10)
+            tr = stage1.Stage1Trainer(stage1.Stage1Config(), fused=fz)
+            torch.cuda.synchronize(); t0 = time.perf_counter(); tr.train(500); torch.cuda.synchronize()
+            out[name + "_s_per_500_iters"] = time.perf_counter() - t0
+            out[name + "_final_points"] = tr.gaussians.num_points
+        out["shape"] = "configs/image.yaml stage-1 loop, synthetic RGBA, guidance stubbed, 500 iterations"
+        rows["f2_stage1_loop"] = out
+    except Exception as e:  # noqa: BLE001
+        rows["f2_stage1_loop"] = {"error": repr(e)[:200]}
+    try:        # f3: distCUDA2 against the reference's own CUDA code (oracle/_ref), 100k points of the reference's init ball
+        from oracle import knn_oracle
+        pts = torch.tensor(scene.make_cloud(100000, 0, seed=1, anisotropic=False, sigma=1.0)["means3D"], device=dev)
+        r = {"ours_ms": ev_median(lambda i: distCUDA2(pts), 20), "shape": "100k points"}
+        if os.path.exists(knn_oracle.REF_LIB):
+            knn_oracle.reference_dist_cuda2(pts); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ref = knn_oracle.reference_dist_cuda2(pts)
+            r["reference_simple_knn_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+            r["bit_identical_to_reference"] = bool(torch.equal(ref, distCUDA2(pts)))
+        rows["f3_distCUDA2"] = r
+    except Exception as e:  # noqa: BLE001
+        rows["f3_distCUDA2"] = {"error": repr(e)[:200]}
+    try:        # f4: extract_fields, reference defaults
+        rawf = scene.to_raw_parameters(scene.make_cloud(100000, 0, seed=4, sigma=0.0128))
+        tf = [torch.tensor(rawf[k], device=dev) for k in ("xyz", "opacity", "scaling", "rotation")]
+        rows["f4_extract_fields"] = {"ours_ms": ev_median(lambda i: fields.extract_fields(*tf, resolution=128), 5), "shape": "100k Gaussians, 128^3, 16^3 blocks"}
+    except Exception as e:  # noqa: BLE001
+        rows["f4_extract_fields"] = {"error": repr(e)[:200]}
+    return rows
 
 
 def time_cpu_oracle(a, cloud, cams, ups, steps, warmup):
@@ -448,6 +545,8 @@ def run_ours(a, rank, world, local_rank):
         out["cpu_baseline"] = {"value": val, "unit": "splats/s", "cores": threads, "kind": "port",
                                "sample": "2 full views fwd+bwd of the same workload (oracle/dgr_oracle.c, float32, OpenMP)",
                                "seconds_per_view": sec, "cpu": cpu_model()}
+    if world == 1 and not a.no_rows:
+        out["next_rows"] = measure_next_rows(dev)
     print(json.dumps(out), flush=True)
 
 

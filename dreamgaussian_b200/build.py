@@ -74,5 +74,48 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+# ---- the compiled PyTorch host layer over the C ABI (csrc/dgr_torch.cpp): g++ only, links libdgr_b200.so
+HOST_PATH = os.path.join(LIB_DIR, "dgr_torch_host.so")
+HOST_HASH = os.path.join(LIB_DIR, "dgr_torch_host.srchash")
+
+
+def _host_hash():
+    import hashlib
+    import torch
+    h = hashlib.sha256(torch.__version__.encode())
+    for s in (os.path.join(CSRC, "dgr_torch.cpp"), os.path.join(HERE, "..", "include", "dgr_b200.h")):
+        with open(s, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def build_host(force=False):
+    """g++ csrc/dgr_torch.cpp -> lib/dgr_torch_host.so (pybind11 module `dgr_torch_host`).  Returns the path."""
+    build()
+    if not force and os.path.exists(HOST_PATH) and os.path.exists(HOST_HASH) and open(HOST_HASH).read().strip() == _host_hash():
+        return HOST_PATH
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension as ce
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    inc = ce.include_paths() + [sysconfig.get_paths()["include"], "/usr/local/cuda/include"]
+    libdirs = ce.library_paths()
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=dgr_torch_host", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI), "-w",
+           os.path.join(CSRC, "dgr_torch.cpp"), "-o", HOST_PATH]
+    cmd += ["-I" + i for i in inc] + ["-L" + d for d in libdirs] + ["-L" + LIB_DIR]
+    cmd += ["-ltorch", "-ltorch_cpu", "-lc10", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda", "-ldgr_b200", "-Wl,-rpath,$ORIGIN"]
+    cmd += ["-Wl,-rpath," + d for d in libdirs]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    with open(os.path.join(LIB_DIR, "build_host.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + proc.stdout)
+    if proc.returncode != 0:
+        raise RuntimeError("g++ failed on dgr_torch.cpp:\n" + proc.stdout[-6000:])
+    with open(HOST_HASH, "w") as f:
+        f.write(_host_hash())
+    return HOST_PATH
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

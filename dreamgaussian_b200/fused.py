@@ -36,6 +36,12 @@ class DensifyStats:
 class _RasterizeRaw(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, means2D, features_dc, features_rest, opacity_raw, scaling_raw, rotation_raw, raster_settings, stats):
+        if _r._FAST is not None:
+            color, radii, depth, alpha, state = _r.forward_impl(raster_settings, xyz, features_dc, None, opacity_raw, scaling_raw, rotation_raw,
+                                                                None, sh_rest=features_rest, activations=True)
+            ctx.state, ctx.stats = state, stats
+            ctx.mark_non_differentiable(radii)
+            return color, radii, depth, alpha
         xyz = _r._dev_f32(xyz, "xyz")
         dc = _r._dev_f32(features_dc, "features_dc")
         rest = _r._opt(features_rest, "features_rest")
@@ -51,6 +57,10 @@ class _RasterizeRaw(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
         state = ctx.state
+        if state.fast is not None:
+            stats = ctx.stats.as_tuple() if ctx.stats is not None else (None, None, None)
+            g = _r._FAST.backward(state.fast, grad_color, grad_depth, grad_alpha, False, [], *stats)
+            return g[0], g[1], g[2], g[8], g[4], g[5], g[6], None, None
         xyz, dc, _, op, sc, rot, _, rest = state.tensors
         P = state.frame.P
         f32 = dict(dtype=torch.float32, device=xyz.device)

@@ -20,6 +20,49 @@ import torch.nn as nn
 from . import _lib
 
 
+def _load_fast():
+    """The compiled host layer (csrc/dgr_torch.cpp -> lib/dgr_torch_host.so): same C-ABI calls, ~10x less host time per
+    call than ctypes.  Optional: without it (or with DGR_NO_FASTHOST=1) the ctypes path below does the same work."""
+    import importlib.util
+    import os
+    if os.environ.get("DGR_NO_FASTHOST") == "1":
+        return None
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "dgr_torch_host.so")
+    if not os.path.exists(path):
+        return None
+    try:
+        _lib.load()
+        spec = importlib.util.spec_from_file_location("dgr_torch_host", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod if mod.abi_version() == 2 else None
+    except Exception:  # noqa: BLE001  (a torch / compiler mismatch: fall back to ctypes, never to a CPU path)
+        return None
+
+
+_FAST = _load_fast()
+
+
+def set_fast_host(enabled: bool):
+    """Switch between the compiled host layer and the ctypes one (tests exercise both)."""
+    global _FAST
+    _FAST = _load_fast() if enabled else None
+    return _FAST is not None
+
+
+def get_capacity_hint(device_index, P, H, W):
+    if _FAST is not None:
+        return _FAST.get_hint(device_index, P, H, W)
+    return _CAPACITY_HINT.get((device_index, P, H, W))
+
+
+def set_capacity_hint(device_index, P, H, W, cap, big):
+    if _FAST is not None:
+        _FAST.set_hint(device_index, P, H, W, cap, big)
+    else:
+        _CAPACITY_HINT[(device_index, P, H, W)] = (cap, big)
+
+
 class GaussianRasterizationSettings(NamedTuple):
     image_height: int
     image_width: int
@@ -108,7 +151,7 @@ def _stream_ptr(device):
 
 class ForwardState:
     """Everything one forward leaves behind for its backward (upstream: ctx + geom/binning/img buffers)."""
-    __slots__ = ("rs", "frame", "num_rendered", "capacity", "geom", "binning", "image", "radii", "alpha", "tensors")
+    __slots__ = ("rs", "frame", "num_rendered", "capacity", "geom", "binning", "image", "radii", "alpha", "tensors", "fast")
 
 
 def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D, sh_rest=None, activations=False):
@@ -118,6 +161,16 @@ def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, 
     No host round trip sits between the kernels: the instance buffer is sized from a per-shape capacity hint, every
     kernel of the forward is enqueued, and only then does the host wait for the (early) instance-count event.  If the
     guess was too small, stage 2 is re-run with a large enough buffer (the kernels clip safely to the capacity)."""
+    if _FAST is not None:
+        color, radii, depth, alpha, cst = _FAST.forward(
+            int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy), float(rs.scale_modifier), int(rs.sh_degree),
+            bool(rs.prefiltered), bool(rs.debug), rs.bg, rs.viewmatrix, rs.projmatrix, rs.campos, means3D, sh, colors_precomp, opacities,
+            scales, rotations, cov3D, sh_rest, bool(activations))
+        state = ForwardState()
+        state.fast, state.rs, state.num_rendered, state.capacity = cst, rs, cst.num_rendered, cst.capacity
+        state.radii, state.alpha = radii, None
+        state.tensors = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3D, sh_rest)
+        return color, radii, depth, alpha, state
     lib = _lib.load()
     dev = means3D.device
     with torch.cuda.device(dev):
@@ -152,8 +205,11 @@ def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, 
             rerun = 2                                   # DGR_FLAG_RERUN
         _CAPACITY_HINT[key] = (max(int(n_inst * 1.25) + 4096, 65536), n_big > 0)
     state = ForwardState()
+    state.fast = None
     state.rs, state.frame, state.num_rendered, state.capacity = rs, fr, n_inst, cap
-    state.geom, state.binning, state.image, state.radii, state.alpha = geom, binning, image, radii, alpha
+    # alpha is a differentiable OUTPUT: storing it here would close the cycle state -> alpha -> grad_fn -> ctx -> state and leave
+    # ~100 MB of scratch per call to the cyclic garbage collector (the C ABI's out_alpha argument is unused)
+    state.geom, state.binning, state.image, state.radii, state.alpha = geom, binning, image, radii, None
     state.tensors = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3D, sh_rest)
     return color, radii, depth, alpha, state
 
@@ -180,6 +236,10 @@ def backward_impl(state, grad_color, grad_depth, grad_alpha, d_means3D, d_means2
                   d_cov, accumulate=False, d_sh_rest=None, densify=None):
     """Runs the backward through the C ABI, writing (or accumulating) into the given gradient tensors.
     densify = (xyz_gradient_accum, denom, max_radii2D) float32 [P] tensors (any may be None) updated in the same kernel."""
+    if state.fast is not None:
+        _FAST.backward(state.fast, grad_color, grad_depth, grad_alpha, bool(accumulate),
+                       [d_means3D, d_means2D, d_sh, d_col, d_opac, d_scales, d_rot, d_cov, d_sh_rest], *(densify or (None, None, None)))
+        return
     lib = _lib.load()
     fr = state.frame
     dev = state.radii.device
@@ -209,6 +269,9 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
         state = ctx.state
+        if state.fast is not None:
+            g = _FAST.backward(state.fast, grad_color, grad_depth, grad_alpha, False, [], None, None, None)      # undefined -> None
+            return g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7], None
         means3D, sh, colors_precomp, opacities, scales, rotations, cov3D, _ = state.tensors
         dev = means3D.device
         P, M = state.frame.P, state.frame.M

@@ -84,3 +84,19 @@ def test_product_never_imports_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h")):
                     txt = open(os.path.join(dirpath, f)).read()
                     assert "oracle" not in txt.replace("no oracle", ""), "%s mentions the oracle" % os.path.join(dirpath, f)
+
+
+def test_compiled_host_layer_builds_loads_and_has_no_cpu_path():
+    """csrc/dgr_torch.cpp -> lib/dgr_torch_host.so: the PyTorch binding of the same C-ABI calls (no arithmetic of its own)."""
+    from dreamgaussian_b200 import rasterizer as R
+    path = build.build_host()
+    assert os.path.exists(path)
+    assert R.set_fast_host(True), "the compiled host layer did not load"
+    mod = R._FAST
+    assert mod.abi_version() == 2 and all(hasattr(mod, n) for n in ("forward", "backward", "State", "get_hint", "set_hint"))
+    z = torch.zeros(3)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        mod.forward(8, 8, 0.5, 0.5, 1.0, 0, False, False, z, torch.zeros(16), torch.zeros(16), z, torch.zeros(4, 3), None,
+                    torch.zeros(4, 3), torch.zeros(4, 1), torch.zeros(4, 3), torch.zeros(4, 4), None, None, False)
+    mod.set_hint(0, 123, 8, 8, 4096, True)
+    assert mod.get_hint(0, 123, 8, 8) == (4096, True) and mod.get_hint(0, 124, 8, 8) is None

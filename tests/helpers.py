@@ -137,7 +137,7 @@ def run_cuda_raw(settings, raw, grads, stats=None, device="cuda"):
                 radii=radii.cpu().numpy(), grads=g)
 
 
-def compare(cu, ref, check_grads=True):
+def compare(cu, ref, check_grads=True, max_ambig_frac=MAX_AMBIG_FRAC, ambig_atol=AMBIG_ATOL):
     """Returns (ok, report dict). cu = CUDA outputs (float32), ref = oracle outputs with flags."""
     rep = {}
     ok = True
@@ -145,7 +145,7 @@ def compare(cu, ref, check_grads=True):
     ag = ref["ambig_g"]
     rep["ambig_px_frac"] = float(apx.mean()) if apx.size else 0.0
     rep["ambig_g_frac"] = float((ag != 0).mean()) if ag.size else 0.0
-    if rep["ambig_px_frac"] > MAX_AMBIG_FRAC:
+    if rep["ambig_px_frac"] > max_ambig_frac:
         ok = False
     for name in ("color", "depth", "alpha"):
         d = np.abs(cu[name].astype(np.float64) - ref[name])
@@ -155,7 +155,7 @@ def compare(cu, ref, check_grads=True):
         amb = d[m].max() if m.any() else 0.0
         rep[name + "_err"] = float(clean / scale)
         rep[name + "_err_ambig"] = float(amb / scale)
-        if clean / scale > IMG_ATOL or amb / scale > AMBIG_ATOL:
+        if clean / scale > IMG_ATOL or amb / scale > ambig_atol:
             ok = False
     rad_bad = (cu["radii"] != ref["radii"]) & ((ag & 4) == 0)
     rep["radii_mismatch"] = int(rad_bad.sum())

@@ -1,0 +1,20 @@
+"""Full-size parity reports for shapes that are not (yet) in the test suite: one view of BASELINE.json configs[2]
+(500k / 512^2, long per-pixel lists -> many decision-ambiguous pixels) and configs[1] at the reference's initial opacity.
+Prints the complete tests/helpers.compare report as JSON lines; writes gpurun_out/extra_parity.json."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers as h
+
+out = {}
+for name, kw, g_kw, cmp_kw in (
+        ("cfg3_view_500k_512", dict(P=500000, res=512, deg=3, sigma=0.0075, elev=-12, azim=75), dict(depth=False), dict(max_ambig_frac=0.25, ambig_atol=0.15)),
+        ("cfg2_init_opacity", dict(P=100000, res=800, deg=3, opacity="init", elev=20, azim=-60), dict(), dict(max_ambig_frac=0.25))):
+    s, i = h.make_case(**kw)
+    g = h.upstream_grads(s["image_height"], s["image_width"], **g_kw)
+    ok, rep = h.compare(h.run_cuda(s, i, g), h.run_oracle(s, i, g), **cmp_kw)
+    rep["ok"] = bool(ok)
+    out[name] = rep
+    print(name, json.dumps(rep), flush=True)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "extra_parity.json"), "w"), indent=1)

@@ -78,10 +78,10 @@ def test_no_cpu_path():
 
 def test_product_never_imports_the_oracle():
     """The oracle is test infrastructure: nothing under dreamgaussian_b200/ or diff_gaussian_rasterization/ may use it."""
-    for pkg in ("dreamgaussian_b200", "diff_gaussian_rasterization"):
+    for pkg in ("dreamgaussian_b200", "diff_gaussian_rasterization", "simple_knn"):
         for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
             for f in files:
-                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                     txt = open(os.path.join(dirpath, f)).read()
                     assert "oracle" not in txt.replace("no oracle", ""), "%s mentions the oracle" % os.path.join(dirpath, f)
 

@@ -9,6 +9,7 @@ import os
 from . import build as _build
 
 c_f32p = ctypes.c_void_p  # device pointers travel as integers
+ABI_VERSION = 2          # include/dgr_b200.h DGR_ABI_VERSION
 
 
 class DgrSettings(ctypes.Structure):
@@ -126,7 +127,7 @@ def load():
     lib.dgr_profile_enable.argtypes = [ctypes.c_int]
     lib.dgr_profile_collect.restype = ctypes.c_int
     lib.dgr_profile_collect.argtypes = [ctypes.c_char_p, ctypes.c_size_t, vp, ctypes.c_int]
-    if lib.dgr_abi_version() != 2:
+    if lib.dgr_abi_version() != ABI_VERSION:
         raise RuntimeError("libdgr_b200.so ABI version mismatch")
     _lib = lib
     tune = os.environ.get("DGR_TUNING")        # "ppl_fwd,ppl_bwd,tile_order" for experiments

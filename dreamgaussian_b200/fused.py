@@ -57,6 +57,11 @@ class _RasterizeRaw(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
         state = ctx.state
+        # the statistics describe the RENDER, not the backward call: a retain_graph / second backward of the same forward
+        # must not count the view twice (gs_renderer.py:625-627 runs once per render)
+        if getattr(state, "stats_applied", False):
+            ctx.stats = None
+        state.stats_applied = True
         if state.fast is not None:
             stats = ctx.stats.as_tuple() if ctx.stats is not None else (None, None, None)
             g = _r._FAST.backward(state.fast, grad_color, grad_depth, grad_alpha, False, [], *stats)

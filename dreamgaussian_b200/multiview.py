@@ -109,6 +109,10 @@ class ViewShardedRasterizer:
         """upstream[i] = (dL_dcolor [3,H,W] or None, dL_ddepth or None, dL_dalpha or None) for local view i."""
         g = self.grads.views
         images = []
+        if len(settings) == 0:
+            # a rank without a view this iteration (fewer views than ranks) contributes ZERO to the all-reduce; without this
+            # its buffer would still hold the previous iteration's reduced sum
+            self.grads.storage.zero_()
         for i, (rs, up) in enumerate(zip(settings, upstream)):
             color, radii, depth, alpha, state = _r.forward_impl(
                 rs, params["means3D"], params["shs"], None, params["opacities"], params["scales"], params["rotations"], None)

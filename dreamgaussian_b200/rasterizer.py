@@ -31,12 +31,20 @@ def _load_fast():
     if not os.path.exists(path):
         return None
     try:
+        from . import build as _build
+        if not os.path.exists(_build.HOST_HASH) or open(_build.HOST_HASH).read().strip() != _build._host_hash():
+            import warnings
+            warnings.warn("dgr_torch_host.so is stale (csrc/dgr_torch.cpp or include/dgr_b200.h changed since it was built): "
+                          "using the ctypes host layer; run dreamgaussian_b200/build.py", RuntimeWarning)
+            return None
         _lib.load()
         spec = importlib.util.spec_from_file_location("dgr_torch_host", path)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
-        return mod if mod.abi_version() == 2 else None
-    except Exception:  # noqa: BLE001  (a torch / compiler mismatch: fall back to ctypes, never to a CPU path)
+        return mod if mod.abi_version() == _lib.ABI_VERSION else None
+    except Exception as e:  # noqa: BLE001  (a torch / compiler mismatch: fall back to ctypes, never to a CPU path)
+        import warnings
+        warnings.warn("dgr_torch_host.so could not be loaded (%r): using the ctypes host layer" % (e,), RuntimeWarning)
         return None
 
 
@@ -151,7 +159,8 @@ def _stream_ptr(device):
 
 class ForwardState:
     """Everything one forward leaves behind for its backward (upstream: ctx + geom/binning/img buffers)."""
-    __slots__ = ("rs", "frame", "num_rendered", "capacity", "geom", "binning", "image", "radii", "alpha", "tensors", "fast")
+    __slots__ = ("rs", "frame", "num_rendered", "capacity", "geom", "binning", "image", "radii", "alpha", "tensors", "fast",
+                 "stats_applied")
 
 
 def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D, sh_rest=None, activations=False):

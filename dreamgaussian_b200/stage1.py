@@ -231,6 +231,16 @@ class GaussianModelB200:
     def prune(self, min_opacity, extent, max_screen_size):
         self.prune_points(self._prune_mask(min_opacity, extent, max_screen_size))
 
+    def reset_opacity(self):
+        """gs_renderer.py:417-420 + replace_tensor_to_optimizer :464-477: opacity = inverse_sigmoid(min(sigmoid(o), 0.01)) and
+        that group's Adam moments zeroed (torch keeps the group's step count: `stored_state["step"]` is left alone)."""
+        with torch.no_grad():
+            o = torch.sigmoid(self.p["opacity"].detach())
+            o = torch.min(o, torch.full_like(o, 0.01))
+            self.p["opacity"] = torch.log(o / (1 - o)).contiguous().requires_grad_(True)
+            self.exp_avg["opacity"] = torch.zeros_like(self.p["opacity"])
+            self.exp_avg_sq["opacity"] = torch.zeros_like(self.p["opacity"])
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 class Stage1Config(NamedTuple):
@@ -352,7 +362,8 @@ class Stage1Trainer:
                     st.denom[vis] += 1
             if self.step % cfg.densification_interval == 0:
                 g.densify_and_prune(cfg.densify_grad_threshold, min_opacity=0.01, extent=4, max_screen_size=1)
-            # opacity_reset_interval = 700 > iters: never fires in this configuration (image.yaml:79)
+            if self.step % cfg.opacity_reset_interval == 0:          # main.py:285-286 (700 > 500 iterations in image.yaml)
+                g.reset_opacity()
         self.losses.append(loss.detach())
         return loss
 

@@ -80,6 +80,21 @@ def main():
     for k, v in state_of(gm).items():
         out["after_densify_" + k] = v
     print("points: %d -> %d" % (P, gm.get_xyz.shape[0]))
+    # reset_opacity (gs_renderer.py:417-420) followed by one more optimiser step: the opacity group restarts from zero
+    # moments but keeps its step count (replace_tensor_to_optimizer :464-477 leaves stored_state["step"] alone)
+    gm.reset_opacity()
+    for k, v in state_of(gm).items():
+        out["after_reset_" + k] = v
+    gm.update_learning_rate(3)
+    n = gm.get_xyz.shape[0]
+    shapes = dict(xyz=(n, 3), f_dc=(n, 1, 3), f_rest=(n, 3, 3), opacity=(n, 1), scaling=(n, 3), rotation=(n, 4))
+    for grp in gm.optimizer.param_groups:
+        g3 = rng.normal(0, 0.1, shapes[grp["name"]]).astype(np.float32)
+        out["grad3_" + grp["name"]] = g3
+        grp["params"][0].grad = torch.tensor(g3)
+    gm.optimizer.step()
+    for k, v in state_of(gm).items():
+        out["after_reset_adam_" + k] = v
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT) >> 10, "KiB")
 

@@ -100,3 +100,18 @@ def test_compiled_host_layer_builds_loads_and_has_no_cpu_path():
                     torch.zeros(4, 3), torch.zeros(4, 1), torch.zeros(4, 3), torch.zeros(4, 4), None, None, False)
     mod.set_hint(0, 123, 8, 8, 4096, True)
     assert mod.get_hint(0, 123, 8, 8) == (4096, True) and mod.get_hint(0, 124, 8, 8) is None
+
+
+def test_reference_caller_imports_against_the_drop_in_packages():
+    """oracle/ref_caller.py: the reference's gs_renderer.py (source or its byte code in oracle/_ref/pyc) binds to THIS repo's
+    diff_gaussian_rasterization and simple_knn._C; the GPU run is tests/test_reference_caller_gpu.py."""
+    import pytest
+    from oracle import ref_caller
+    ref_caller.build_ref_pyc()
+    if not ref_caller.available():
+        pytest.skip("no reference caller available on this machine")
+    cam_utils, gs, sh_utils = ref_caller.load()
+    import diff_gaussian_rasterization as ours
+    import simple_knn._C as knn
+    assert gs.GaussianRasterizer is ours.GaussianRasterizer and gs.distCUDA2 is knn.distCUDA2
+    assert hasattr(gs, "Renderer") and hasattr(gs, "MiniCam") and hasattr(cam_utils, "orbit_camera")

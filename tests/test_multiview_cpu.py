@@ -84,3 +84,32 @@ def test_two_rank_gloo_all_reduce_sums_view_gradients(tmp_path):
         for k, view in fg.views.items():
             view += torch.tensor(ref["grads"][k].astype(np.float32)).view_as(view)
     np.testing.assert_allclose(got, fg.flat.numpy(), rtol=1e-5, atol=1e-5 * np.abs(fg.flat.numpy()).max())
+
+
+def _worker_empty_shard(rank, world, port, out_dir):
+    """a rank with no view this iteration must contribute zeros, not last iteration's reduced sum."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P, M = 50, 4
+        vsr = multiview.ViewShardedRasterizer(P, M, "cpu")
+        results = []
+        for it in range(2):                                     # two iterations with ONE view for two ranks
+            mine = multiview.shard_views(1, rank, world)
+            if mine:
+                vsr.grads.flat.fill_(1.0 + it)                    # stands for render_views() overwriting with this view's gradient
+            else:
+                vsr.render_views({}, [], [])                    # no local view
+            results.append(vsr.all_reduce().clone())
+        torch.save(results, os.path.join(out_dir, "r%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_rank_without_a_view_contributes_zero(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker_empty_shard, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        res = torch.load(os.path.join(str(tmp_path), "r%d.pt" % r))
+        assert float(res[0].min()) == 1.0 and float(res[0].max()) == 1.0
+        assert float(res[1].min()) == 2.0 and float(res[1].max()) == 2.0      # would be 3.0 with the stale buffer

@@ -84,3 +84,27 @@ def test_synthetic_input_and_guidance_stub_contract():
     loss = g.train_step(x, [0], [0], [0], step_ratio=0.5)
     loss.backward()
     assert loss.dim() == 0 and x.grad is not None and float(x.grad.abs().sum()) > 0
+
+
+def test_reset_opacity_matches_the_reference_method_and_keeps_the_step_count():
+    """gs_renderer.py:417-420, 464-477 (main.py:285-286): golden = the reference's reset_opacity after its densify_and_prune,
+    then one more torch.optim.Adam step."""
+    m = _model_from_golden()
+    _two_adam_steps(m)
+    m.stats.xyz_gradient_accum = torch.tensor(GOLD["stats_xyz_gradient_accum"]).reshape(-1)
+    m.stats.denom = torch.tensor(GOLD["stats_denom"]).reshape(-1)
+    m.stats.max_radii2D = torch.tensor(GOLD["stats_max_radii2D"]).reshape(-1)
+    noise = torch.tensor(GOLD["split_noise"])
+
+    class Noise:
+        def to(self, stds):
+            return noise[: stds.shape[0]].to(stds)
+    m.densify_and_prune(0.01, min_opacity=0.01, extent=4, max_screen_size=1, noise=Noise())
+    m.reset_opacity()
+    check_against(m, "after_reset_", rtol=3e-6, atol=1e-7)
+    assert float(torch.sigmoid(m.p["opacity"]).max()) <= 0.01 + 1e-7 and not m.exp_avg["opacity"].any()
+    m.update_learning_rate(3)
+    for k in NAMES:
+        m.p[k].grad = torch.tensor(GOLD["grad3_" + k])
+    m.optimizer_step()
+    check_against(m, "after_reset_adam_", rtol=5e-6, atol=1e-7)

@@ -26,27 +26,47 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
+# BASELINE.json configs that are bench workloads (configs[0] and [3] are parity / loop cases: tests/, next_rows.f2)
+WORKLOADS = {
+    "cfg2": dict(points=100000, res=800, views_per_gpu=1, views=8, steps=1000,
+                 what="BASELINE.json configs[1]: 100k Gaussians, 800x800, SH degree 3, forward+backward, one view per GPU per step"),
+    "cfg3": dict(points=500000, res=512, views_per_gpu=8, views=64, steps=60,
+                 what="BASELINE.json configs[2]: 500k Gaussians, 512x512, 64 views per iteration sharded 8 per GPU (8 views per GPU "
+                      "per step accumulate into the flat gradient, one all-reduce per step)"),
+    "cfg5": dict(points=2000000, res=1600, views_per_gpu=1, views=8, steps=100,
+                 what="BASELINE.json configs[4]: 2M Gaussians, 1600x1600, SH degree 3, forward+backward, one view per GPU per step"),
+}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--points", type=int, default=100000)
-    ap.add_argument("--res", type=int, default=800)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="cfg2 = the metric's configuration (default)")
+    ap.add_argument("--points", type=int, default=None)
+    ap.add_argument("--res", type=int, default=None)
+    ap.add_argument("--views-per-gpu", type=int, default=None)
     ap.add_argument("--sh-degree", type=int, default=3)
     ap.add_argument("--opacity", default="trained", choices=["trained", "init"])
-    ap.add_argument("--views", type=int, default=8, help="size of the fixed camera set that steps cycle through")
+    ap.add_argument("--views", type=int, default=None, help="size of the fixed camera set that steps cycle through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rows", action="store_true", help="skip the short measurements of the SURVEY §8f rows (f1-f4)")
     ap.add_argument("--seed", type=int, default=0)
-    return ap.parse_args()
+    a = ap.parse_args()
+    w = WORKLOADS[a.workload]
+    for k in ("points", "res", "views_per_gpu", "views", "steps"):
+        if getattr(a, k) is None:
+            setattr(a, k, w[k])
+    return a
 
 
 def workload_name(a):
-    return "%dk Gaussians, %dx%d, SH degree %d, forward+backward, opacity=%s, anisotropic" % (
-        a.points // 1000, a.res, a.res, a.sh_degree, a.opacity)
+    return "%dk Gaussians, %dx%d, SH degree %d, forward+backward, opacity=%s, anisotropic%s" % (
+        a.points // 1000, a.res, a.res, a.sh_degree, a.opacity,
+        "" if a.views_per_gpu == 1 else ", %d views per GPU per step" % a.views_per_gpu)
 
 
 def algorithmic_bytes(P, M, H, W, n_inst):
@@ -58,9 +78,9 @@ def kernel_algorithmic_bytes(name, P, M, H, W, n_inst):
     """Per-kernel algorithmic bytes (what the kernel must read + write once), DESIGN.md §Kernels."""
     px = H * W
     table = {
-        "preprocess_fwd": P * (44 + 12 * M) + P * (4 + 48 + 4) + n_inst * 4, # inputs; radii + record + touched; histogram
-        "tile_scan": (H // 16 + 1) * (W // 16 + 1) * 16,                    # counts in; ranges + cursor out
-        "emit_instances": P * 52 + n_inst * 12,                             # record + touched; cursor atomics + key
+        "preprocess_fwd": P * (44 + 12 * M) + P * (4 + 48 + 4),              # inputs; radii + record + touched
+        "tile_scan": (H // 16 + 1) * (W // 16 + 1) * 24,                    # counts in; ranges + cursor + order out
+        "emit_instances": P * 12 + n_inst * 8,                              # aabb + depth + touched; keys
         "tile_sort_gather": n_inst * (8 + 4 + 48 + 48),                     # key in; id out; record gather + sorted record
         "tile_sort_gather_big": n_inst * (8 + 4 + 48 + 48),                 # the big-tile walker does the same per instance (upper bound: all instances)
         "render_fwd": n_inst * 48 + px * 28,                                 # sorted records; rgb+depth+alpha+n_contrib+T
@@ -130,7 +150,10 @@ class ClockSampler:
 
 def build_scene(a):
     from dreamgaussian_b200 import scene
-    cloud = scene.make_cloud(a.points, a.sh_degree, seed=a.seed, opacity=a.opacity, anisotropic=True)
+    # base scale = 3-NN distance of the cloud (kd-tree) as the reference's initialisation derives it; above 500k points its
+    # closed form 0.595 P^(-1/3) (fitted at 5k / 100k / 500k to 1 %) replaces the minutes-long kd-tree query
+    sigma = None if a.points <= 500000 else 0.595 * a.points ** (-1.0 / 3.0)
+    cloud = scene.make_cloud(a.points, a.sh_degree, seed=a.seed, opacity=a.opacity, anisotropic=True, sigma=sigma)
     cams = scene.bench_views(a.views, a.res, a.res)
     rng = np.random.default_rng(a.seed + 17)
     ups = [(rng.normal(size=(3, a.res, a.res)).astype(np.float32), None, rng.normal(size=(1, a.res, a.res)).astype(np.float32))
@@ -162,6 +185,66 @@ def host_threads():
     except Exception:
         pass
     return max(1, n)
+
+
+def measure_other_shapes(dev):
+    """Short device-timed measurements of the OTHER BASELINE.json shapes and of configs[1] at the reference's initial opacity
+    (0.1 everywhere: no early termination — the hard case), so that the default run carries them next to the headline line.
+    Same protocol as the headline (CUDA events per step, L2 flushed between steps), fewer steps."""
+    import torch
+    from dreamgaussian_b200 import _lib, multiview
+    from dreamgaussian_b200.rasterizer import GaussianRasterizationSettings
+    lib = _lib.load()
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
+    rows = {}
+    shapes = (("cfg2_init_opacity", "cfg2", dict(opacity="init"), 40),
+              ("cfg3_8_views_per_gpu", "cfg3", {}, 6),
+              ("cfg5", "cfg5", {}, 12))
+    for key, wl, over, steps in shapes:
+        try:
+            a = argparse.Namespace(sh_degree=3, opacity="trained", seed=0, workload=wl, **{k: WORKLOADS[wl][k] for k in ("points", "res", "views_per_gpu", "views")})
+            for k, v in over.items():
+                setattr(a, k, v)
+            cloud, cams, ups = build_scene(a)
+            t = lambda x: torch.tensor(np.asarray(x, np.float32), device=dev)
+            params = {k: t(v) for k, v in cloud.items()}
+            bg = t(np.ones(3, np.float32))
+            settings = [GaussianRasterizationSettings(
+                image_height=a.res, image_width=a.res, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg, scale_modifier=1.0,
+                viewmatrix=t(c.world_view_transform), projmatrix=t(c.full_proj_transform), sh_degree=3,
+                campos=t(c.camera_center), prefiltered=False, debug=False) for c in cams]
+            ups_d = [(t(u[0]), None, t(u[2])) for u in ups]
+            vsr = multiview.ViewShardedRasterizer(a.points, 16, dev)
+            vpg = a.views_per_gpu
+
+            def step(i):
+                vs = [(i * vpg + k) % len(settings) for k in range(vpg)]
+                vsr.render_views(params, [settings[v] for v in vs], [ups_d[v % len(ups_d)] for v in vs])
+            for i in range(3):
+                step(i)
+            torch.cuda.synchronize(dev)
+            evs = []
+            for i in range(steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); step(3 + i); e1.record(); evs.append((e0, e1))
+            torch.cuda.synchronize(dev)
+            ms = float(np.mean([x.elapsed_time(y) for x, y in evs]))
+            lib.dgr_profile_enable(1)
+            for i in range(2):
+                flush.zero_(); step(i)
+            torch.cuda.synchronize(dev)
+            kern = {}
+            for name, v in _lib.profile_collect():
+                kern.setdefault(name, []).append(v)
+            lib.dgr_profile_enable(0)
+            rows[key] = {"workload": workload_name(a), "ms_per_step": ms, "splats_per_s": a.points * vpg / (ms * 1e-3), "steps": steps,
+                         "kernels_us_per_view": {k: round(float(np.sum(v)) / (2 * vpg) * 1e3, 1) for k, v in kern.items()}}
+            del vsr, params, settings, ups_d
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            rows[key] = {"error": repr(e)[:300]}
+    return rows
 
 
 def measure_next_rows(dev):
@@ -311,11 +394,54 @@ def run_reference(a, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def collective_check(vsr, dev, rank, world):
+    """N > 1, before anything is timed: the library's own all-reduce on a buffer of per-rank noise must agree with NCCL's
+    all_reduce of the same data and must leave the same bits on every rank."""
+    import torch
+    import torch.distributed as dist
+    g = torch.Generator(device=dev); g.manual_seed(4321 + rank)
+    n = vsr.grads.flat.numel()
+    src = torch.randn(n, device=dev, generator=g)
+    ref = src.clone()
+    dist.all_reduce(ref)                                           # NCCL
+    vsr.grads.flat.copy_(src)
+    torch.cuda.synchronize(dev); dist.barrier()
+    got = vsr.all_reduce().clone()
+    torch.cuda.synchronize(dev)
+    diff = float((got - ref).abs().max()); scale = float(ref.abs().max())
+    hi, lo = got.clone(), got.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX); dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    same = bool(torch.equal(hi, lo))
+    ok = torch.tensor([1.0 if (diff <= 1e-5 * scale and same) else 0.0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    vsr.grads.data.zero_()
+    torch.cuda.synchronize(dev); dist.barrier()
+    return {"ok": bool(ok.item() == 1.0), "max_abs_diff_vs_nccl": diff, "scale": scale, "identical_on_all_ranks": same,
+            "floats": n, "kernel": vsr.collective}
+
+
+def lib_source_stamp():
+    from dreamgaussian_b200 import build
+    return build.source_hash()[:16]
+
+
+def committed_ncu(kind):
+    """ncu-derived per-launch numbers (DRAM traffic, warp instructions) are only trusted when the capture was taken from
+    the SAME kernel sources: profiles/r2_ncu_kernels.json carries the source hash of the library it profiled."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_kernels.json")))
+        if d.get("lib_source_hash") != lib_source_stamp():
+            return None, "stale (kernel sources changed since the capture)"
+        return d.get(kind), d.get("source")
+    except Exception:
+        return None, "no capture committed"
+
+
 def run_ours(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from dreamgaussian_b200 import _lib, hostmem, multiview
-    from dreamgaussian_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+    from dreamgaussian_b200.rasterizer import GaussianRasterizationSettings
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
@@ -324,8 +450,23 @@ def run_ours(a, rank, world, local_rank):
     lib = _lib.load()
     cloud, cams, ups = build_scene(a)
     P, M, H, W = a.points, (a.sh_degree + 1) ** 2, a.res, a.res
+    vpg = a.views_per_gpu
     t = lambda x: torch.tensor(np.asarray(x, np.float32), device=dev)
-    params = {k: t(v) for k, v in cloud.items()}
+    names = ("means3D", "shs", "opacities", "scales", "rotations")
+    # ONE packed device buffer for the Gaussian inputs (segments 256-byte aligned): the e2e leg fills it with one copy
+    seg, off = {}, 0
+    for k in names:
+        n = int(np.prod(cloud[k].shape))
+        seg[k] = (off, n, cloud[k].shape); off += (n + 63) // 64 * 64
+    packed_floats = off
+
+    def views_of(buf):
+        return {k: buf[o:o + n].view(shape) for k, (o, n, shape) in seg.items()}
+
+    dev_packed = torch.empty((packed_floats,), dtype=torch.float32, device=dev)
+    params = views_of(dev_packed)
+    for k in names:
+        params[k].copy_(t(cloud[k]))
     bg = t(np.ones(3, np.float32))
     settings = [GaussianRasterizationSettings(
         image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg, scale_modifier=1.0,
@@ -335,9 +476,12 @@ def run_ours(a, rank, world, local_rank):
     vsr = multiview.ViewShardedRasterizer(P, M, dev)
     flush_buf = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)    # > 126 MB L2
 
+    def local_views(i):
+        return [((i * world + rank) * vpg + k) % len(settings) for k in range(vpg)]
+
     def step(i):
-        v = (i * world + rank) % len(settings)                               # this rank's view of step i
-        vsr.render_views(params, [settings[v]], [ups_d[v % len(ups_d)]])
+        vs = local_views(i)
+        vsr.render_views(params, [settings[v] for v in vs], [ups_d[v % len(ups_d)] for v in vs])
         if world > 1:
             vsr.all_reduce()
 
@@ -346,12 +490,16 @@ def run_ours(a, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    check = collective_check(vsr, dev, rank, world) if world > 1 else None
+    if check is not None and not check["ok"]:
+        raise SystemExit("bench.py: the library's all-reduce disagrees with NCCL: %r" % (check,))
+
     # nvidia-smi samples every 20 ms; it is started before the warm-up so that even a short timed region is covered
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         sampler.wait_first_sample()
-    for i in range(a.warmup):
+    for i in range(max(a.warmup, 3)):
         step(i)
     barrier()
     n_inst = 0
@@ -376,21 +524,22 @@ def run_ours(a, rank, world, local_rank):
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms_total = float(ms_t.item())
     ms_per_step = ms_total / a.steps
-    value = P * world * a.steps / (ms_total * 1e-3)
+    value = P * vpg * world * a.steps / (ms_total * 1e-3)
 
-    # ---------------- per-kernel CUDA-event timing (separate pass, same workload) ----------------
+    # ---------------- per-kernel CUDA-event timing (separate pass, same workload, this rank's stream) ----------------
     kern = {}
     if rank == 0:
         lib.dgr_profile_enable(1)
-        nprof = min(a.steps, 8)
+        nprof = max(1, min(a.steps, 8))
         for i in range(nprof):
             flush_buf.zero_()
-            vsr.render_views(params, [settings[i % len(settings)]], [ups_d[i % len(ups_d)]])
+            vs = local_views(i)
+            vsr.render_views(params, [settings[v] for v in vs], [ups_d[v % len(ups_d)] for v in vs])
         torch.cuda.synchronize(dev)
         for name, ms in _lib.profile_collect():
             kern.setdefault(name, []).append(ms)
         lib.dgr_profile_enable(0)
-        kern = {k: float(np.mean(v)) for k, v in kern.items()}
+        kern = {k: float(np.sum(v)) / (nprof * vpg) for k, v in kern.items()}       # average per VIEW
         # instance count of the bench views (host read-back the forward already does)
         _, _, _, _, st = __import__("dreamgaussian_b200.rasterizer", fromlist=["forward_impl"]).forward_impl(
             settings[0], params["means3D"], params["shs"], None, params["opacities"], params["scales"], params["rotations"], None)
@@ -399,70 +548,61 @@ def run_ours(a, rank, world, local_rank):
         barrier()
 
     # ---------------- end to end through the public API with HOST buffers ----------------
-    # Every step copies ALL Gaussian inputs from pinned host memory to the device, runs GaussianRasterizer forward +
-    # autograd backward, and copies the loss and ALL input gradients back to pinned host memory.  The three legs run on
-    # three streams over a ring of 3 buffer sets, so step i's compute overlaps step i+1's upload and step i-1's download
-    # (PCIe is full duplex); every byte of every step is moved inside the timed region.
+    # Every step: ONE cudaMemcpyAsync of the packed Gaussian inputs (pinned host -> device), forward + backward of this
+    # rank's views through ViewShardedRasterizer (the call a multi-view user makes; gradients accumulate into the flat buffer,
+    # N > 1: the library's own all-reduce), the loss of the step, then ONE cudaMemcpyAsync of the flat gradient (+ the loss)
+    # back to pinned host memory.  Upload / compute / download of consecutive steps overlap on three streams over a ring of
+    # three buffer sets (PCIe is full duplex); every byte of every step moves inside the timed region.
     e2e = None
     if not a.no_e2e:
-        names = ("means3D", "shs", "opacities", "scales", "rotations")
-        # pinned buffers on the GPU's own NUMA node (dreamgaussian_b200/hostmem.py): cross-socket H2D runs at ~20 GB/s, local at ~53
-        host = {k: hostmem.pinned_like(torch.tensor(cloud[k]), dev) for k in names}
         RING = 3
-        dev_in = [{k: torch.empty_like(host[k], device=dev).requires_grad_(True) for k in names} for _ in range(RING)]
-        grads_host = [{k: hostmem.pinned_empty(host[k].shape, host[k].dtype, dev) for k in names} for _ in range(RING)]
-        loss_host = [hostmem.pinned_empty((1,), torch.float32, dev) for _ in range(RING)]
-        h2d = sum(v.numel() * 4 for v in host.values())
-        d2h = h2d + 4
+        host_in = hostmem.pinned_empty((packed_floats,), torch.float32, dev)          # NUMA-local pinned (hostmem.py)
+        hv = views_of(host_in)
+        for k in names:
+            hv[k].copy_(torch.tensor(cloud[k]))
+        dev_in = [torch.empty((packed_floats,), dtype=torch.float32, device=dev) for _ in range(RING)]
+        dev_views = [views_of(b) for b in dev_in]
+        rings = [vsr] + [multiview.ViewShardedRasterizer(P, M, dev) for _ in range(RING - 1)]
+        nflat = vsr.grads.flat.numel()
+        host_out = [hostmem.pinned_empty((nflat + 64,), torch.float32, dev) for _ in range(RING)]
+        h2d = packed_floats * 4
+        d2h = nflat * 4 + 4
         s_up, s_comp, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         ev_up = [torch.cuda.Event() for _ in range(RING)]
         ev_comp = [torch.cuda.Event() for _ in range(RING)]
         ev_down = [torch.cuda.Event() for _ in range(RING)]
-        m2d = torch.zeros((P, 3), device=dev)
+        losses = [torch.zeros((1,), device=dev) for _ in range(RING)]
 
         def upload(i):
             r = i % RING
             with torch.cuda.stream(s_up):
                 s_up.wait_event(ev_comp[r])                 # the previous user of this buffer set has finished computing
-                with torch.no_grad():
-                    for k in names:
-                        dev_in[r][k].copy_(host[k], non_blocking=True)
+                dev_in[r].copy_(host_in, non_blocking=True)
                 ev_up[r].record(s_up)
 
         def compute(i):
             r = i % RING
-            v = (i * world + rank) % len(settings)
+            vs = local_views(i)
             with torch.cuda.stream(s_comp):
                 s_comp.wait_event(ev_up[r])
                 s_comp.wait_event(ev_down[r])               # its gradients of RING steps ago have been downloaded
-                for k in names:
-                    dev_in[r][k].grad = None
-                color, radii, depth, alpha = GaussianRasterizer(raster_settings=settings[v])(
-                    means3D=dev_in[r]["means3D"], means2D=m2d, shs=dev_in[r]["shs"], opacities=dev_in[r]["opacities"],
-                    scales=dev_in[r]["scales"], rotations=dev_in[r]["rotations"])
-                gC, _, gA = ups_d[v % len(ups_d)]
-                loss = (color * gC).sum() + (alpha * gA).sum()
-                loss.backward()
+                imgs = rings[r].render_views(dev_views[r], [settings[v] for v in vs], [ups_d[v % len(ups_d)] for v in vs], keep_images=True)
+                loss = None
+                for v, (color, radii, depth, alpha) in zip(vs, imgs):
+                    gC, _, gA = ups_d[v % len(ups_d)]
+                    l = (color * gC).sum() + (alpha * gA).sum()
+                    loss = l if loss is None else loss + l
+                losses[r].copy_(loss.reshape(1))
                 if world > 1:
-                    flat = torch.cat([dev_in[r][k].grad.reshape(-1) for k in names])
-                    dist.all_reduce(flat)
-                    o = 0
-                    for k in names:
-                        n = dev_in[r][k].grad.numel()
-                        dev_in[r][k].grad.copy_(flat[o:o + n].view_as(dev_in[r][k].grad)); o += n
+                    rings[r].all_reduce()
                 ev_comp[r].record(s_comp)
-                return loss.detach()
 
-        def download(i, loss):
+        def download(i):
             r = i % RING
             with torch.cuda.stream(s_down):
                 s_down.wait_event(ev_comp[r])
-                for k in names:
-                    g = dev_in[r][k].grad
-                    g.record_stream(s_down)
-                    grads_host[r][k].copy_(g, non_blocking=True)
-                loss.record_stream(s_down)
-                loss_host[r].copy_(loss.reshape(1), non_blocking=True)
+                host_out[r][:nflat].copy_(rings[r].grads.flat, non_blocking=True)
+                host_out[r][nflat:nflat + 1].copy_(losses[r], non_blocking=True)
                 ev_down[r].record(s_down)
 
         def run(nsteps, first):
@@ -470,14 +610,14 @@ def run_ours(a, rank, world, local_rank):
             for i in range(first, first + nsteps):
                 if i + 1 < first + nsteps:
                     upload(i + 1)
-                ls = compute(i)
-                download(i, ls)
+                compute(i)
+                download(i)
 
         for r in range(RING):
             ev_comp[r].record(s_comp); ev_down[r].record(s_down)
         run(max(3, min(a.warmup, 6)), 0)
         barrier()
-        e2e_steps = min(a.steps, 300)
+        e2e_steps = max(3, min(a.steps, 300))
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()                                          # default stream: ordered before the side streams by barrier()
@@ -491,12 +631,28 @@ def run_ours(a, rank, world, local_rank):
         ms_e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": P * world * e2e_steps / (float(ms_e.item()) * 1e-3), "unit": "splats/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": float(ms_e.item()) / e2e_steps, "steps": e2e_steps,
+        # achieved host-link rates: each direction timed alone on this rank, same buffers
+        link = {}
+        for nm, fn, nbytes in (("h2d_gbs", lambda: dev_in[0].copy_(host_in, non_blocking=True), h2d),
+                               ("d2h_gbs", lambda: host_out[0][:nflat].copy_(vsr.grads.flat, non_blocking=True), d2h)):
+            torch.cuda.synchronize(dev)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(5):
+                fn()
+            c1.record(); torch.cuda.synchronize(dev)
+            link[nm] = nbytes * 5 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        step_ms = float(ms_e.item()) / e2e_steps
+        e2e = {"value": P * vpg * world * e2e_steps / (float(ms_e.item()) * 1e-3), "unit": "splats/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": step_ms, "steps": e2e_steps,
                "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / e2e_steps,
-               "host_buffers_numa_local": bool(hostmem.gpu_local_cpus(dev)),
-               "note": "public API (GaussianRasterizer + autograd); inputs from / gradients + loss to pinned host memory every step; "
-                       "upload, compute and download of consecutive steps overlap on 3 streams"}
+               "copies_per_step": {"h2d": 1, "d2h": 2}, "link_gbs_alone": link,
+               "link_gbs_in_pipeline": {"h2d": h2d / (step_ms * 1e-3) / 1e9, "d2h": d2h / (step_ms * 1e-3) / 1e9},
+               "host_buffers_numa_local": bool(hostmem.gpu_local_cpus(dev)), "loss": float(host_out[(100 + e2e_steps - 1) % RING][nflat]),
+               "collective": rings[0].collective if world > 1 else "none",
+               "note": "public API (ViewShardedRasterizer.render_views [+ all_reduce]); packed inputs from / flat gradient + loss to "
+                       "pinned host memory every step, one copy per direction (+4 bytes of loss); upload, compute and download of "
+                       "consecutive steps overlap on 3 streams"}
 
     if rank != 0:
         return
@@ -513,39 +669,46 @@ def run_ours(a, rank, world, local_rank):
     if dom:
         kb = kernel_algorithmic_bytes(dom, P, M, H, W, n_inst)
         ach = kb / (kern[dom] * 1e-3) / 1e9
+        step_bytes = algorithmic_bytes(P, M, H, W, n_inst) * vpg
         roof.update({"kernel": dom, "kernel_ms": kern[dom], "kernel_algorithmic_bytes": kb, "achieved": ach, "frac": ach / peak,
-                     "kernels_ms": kern,
+                     "kernels_ms_per_view": kern,
                      "kernels_frac": {k: (kernel_algorithmic_bytes(k, P, M, H, W, n_inst) or 0) / (v * 1e-3) / 1e9 / peak
                                       for k, v in kern.items()},
-                     "step": {"algorithmic_bytes": algorithmic_bytes(P, M, H, W, n_inst), "n_inst": n_inst,
-                              "achieved": algorithmic_bytes(P, M, H, W, n_inst) / (ms_per_step * 1e-3) / 1e9,
-                              "frac": algorithmic_bytes(P, M, H, W, n_inst) / (ms_per_step * 1e-3) / 1e9 / peak},
-                     "note": "render kernels are issue/MUFU-bound, not HBM-bound (DESIGN.md); fractions are against the HBM copy peak"})
-    if dom:
-        # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of this same workload
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-            if tr.get("workload") == workload_name(a) and dom in tr["bytes_per_launch"]:
-                roof["traffic"] = tr["bytes_per_launch"][dom]
-                roof["traffic_source"] = tr["source"]
-        except Exception:
-            pass
+                     "step": {"algorithmic_bytes": step_bytes, "n_inst": n_inst, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                              "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
+                     "note": "render kernels are issue-bound, not HBM-bound (DESIGN.md): see `issue` for the bound that applies"})
+        tr, src = committed_ncu("dram_bytes_per_launch")
+        if tr and a.workload == "cfg2" and a.opacity == "trained" and dom in tr:
+            roof["traffic"] = tr[dom]
+        roof["traffic_source"] = src
+        # the bound that does apply to the render kernels: warp instructions issued vs the SMs' issue rate
+        inst, src = committed_ncu("warp_inst_per_launch")
+        if inst and a.workload == "cfg2" and a.opacity == "trained" and clocks and clocks.get("sm_mhz"):
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak_issue = sms * 4 * clocks["sm_mhz"] * 1e6              # warp instructions per second (1 per SMSP per clock)
+            roof["issue"] = {"unit": "warp-inst/s", "peak": peak_issue, "source": src,
+                             "kernels": {k: {"warp_inst": inst[k], "achieved": inst[k] / (kern[k] * 1e-3), "frac": inst[k] / (kern[k] * 1e-3) / peak_issue}
+                                         for k in kern if k in inst}}
     out = {
         "metric": "splats/sec fwd+bwd @ %dx%d" % (H, W), "value": value, "unit": "splats/s", "n_gpus": world, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "views_per_gpu_per_step": 1, "view_set": a.views, "l2_flush_between_steps": True,
+        "config": {"workload": workload_name(a), "baseline_config": WORKLOADS[a.workload]["what"], "views_per_gpu_per_step": vpg,
+                   "view_set": a.views, "l2_flush_between_steps": True,
                    "n_inst_view0": n_inst, "parallelism": "view-sharded dp%d, replicated Gaussians, 1 all-reduce of %d MB per step (%s)"
                    % (world, vsr.grads.nbytes() >> 20, vsr.collective) if world > 1 else "single GPU",
+                   "collective_check": check,
                    "wall_ms_per_step_incl_flush": (wall1 - wall0) * 1e3 / a.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "e2e": e2e,
     }
     if world == 1 and not a.no_cpu_baseline:
-        val, sec, threads = time_cpu_oracle(a, cloud, cams, ups, 2, 1)
+        nv = 2 if P <= 200000 else 1
+        val, sec, threads = time_cpu_oracle(a, cloud, cams, ups, nv, 1 if P <= 200000 else 0)
         out["cpu_baseline"] = {"value": val, "unit": "splats/s", "cores": threads, "kind": "port",
-                               "sample": "2 full views fwd+bwd of the same workload (oracle/dgr_oracle.c, float32, OpenMP)",
+                               "sample": "%d full view(s) fwd+bwd of the same workload (oracle/dgr_oracle.c, float32, OpenMP)" % nv,
                                "seconds_per_view": sec, "cpu": cpu_model()}
-    if world == 1 and not a.no_rows:
+    if world == 1 and not a.no_rows and a.workload == "cfg2":
+        out["other_shapes"] = measure_other_shapes(dev)
         out["next_rows"] = measure_next_rows(dev)
     print(json.dumps(out), flush=True)
 

@@ -9,7 +9,7 @@ import os
 from . import build as _build
 
 c_f32p = ctypes.c_void_p  # device pointers travel as integers
-ABI_VERSION = 2          # include/dgr_b200.h DGR_ABI_VERSION
+ABI_VERSION = 3          # include/dgr_b200.h DGR_ABI_VERSION
 
 
 class DgrSettings(ctypes.Structure):
@@ -35,6 +35,11 @@ class DgrAdamGroup(ctypes.Structure):
                 ("lr", ctypes.c_float), ("step", ctypes.c_int32)]
 
 
+class DgrDensifyTensors(ctypes.Structure):
+    _fields_ = [("inp", c_f32p * 6), ("exp_avg_in", c_f32p * 6), ("exp_avg_sq_in", c_f32p * 6),
+                ("out", c_f32p * 6), ("exp_avg_out", c_f32p * 6), ("exp_avg_sq_out", c_f32p * 6), ("width", ctypes.c_int32 * 6)]
+
+
 class DgrImages(ctypes.Structure):
     _fields_ = [("color", c_f32p), ("depth", c_f32p), ("alpha", c_f32p), ("radii", ctypes.c_void_p)]
 
@@ -56,7 +61,7 @@ EXPORTS = (
     "dgr_abi_version", "dgr_last_error", "dgr_launch_count", "dgr_reset_launch_count",
     "dgr_geom_bytes", "dgr_image_bytes", "dgr_binning_bytes",
     "dgr_forward_preprocess", "dgr_forward_render", "dgr_backward", "dgr_mark_visible", "dgr_debug_geom",
-    "dgr_profile_enable", "dgr_profile_collect", "dgr_event_create", "dgr_event_synchronize", "dgr_event_destroy", "dgr_set_tuning", "dgr_peer_allreduce", "dgr_knn_scratch_bytes", "dgr_dist_cuda2", "dgr_fields_scratch_bytes", "dgr_extract_fields", "dgr_adam_step",
+    "dgr_profile_enable", "dgr_profile_collect", "dgr_event_create", "dgr_event_synchronize", "dgr_event_destroy", "dgr_set_tuning", "dgr_peer_allreduce", "dgr_peer_flag_bytes", "dgr_knn_scratch_bytes", "dgr_dist_cuda2", "dgr_fields_scratch_bytes", "dgr_extract_fields", "dgr_adam_step", "dgr_densify_scratch_bytes", "dgr_densify_plan", "dgr_densify_apply",
 )
 
 _lib = None
@@ -95,7 +100,8 @@ def load():
     lib.dgr_forward_preprocess.restype = ctypes.c_int
     lib.dgr_forward_preprocess.argtypes = [ctypes.POINTER(DgrSettings), ctypes.POINTER(DgrGaussians), vp, vp, vp, vp]
     lib.dgr_peer_allreduce.restype = ctypes.c_int
-    lib.dgr_peer_allreduce.argtypes = [vp, i32, i32, u64, u64, vp]
+    lib.dgr_peer_allreduce.argtypes = [vp, i32, i32, u64, u64, vp, ctypes.c_uint32, vp]
+    lib.dgr_peer_flag_bytes.restype = ctypes.c_size_t
     lib.dgr_set_tuning.restype = ctypes.c_int
     lib.dgr_set_tuning.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     lib.dgr_event_create.restype = vp
@@ -119,6 +125,12 @@ def load():
     lib.dgr_extract_fields.argtypes = [i32, vp, vp, vp, vp, i32, i32, ctypes.c_float, vp, vp, vp, vp]
     lib.dgr_adam_step.restype = ctypes.c_int
     lib.dgr_adam_step.argtypes = [ctypes.POINTER(DgrAdamGroup), i32, ctypes.c_double, ctypes.c_double, ctypes.c_double, vp]
+    lib.dgr_densify_scratch_bytes.restype = ctypes.c_size_t
+    lib.dgr_densify_scratch_bytes.argtypes = [i32]
+    lib.dgr_densify_plan.restype = ctypes.c_int
+    lib.dgr_densify_plan.argtypes = [i32, vp, vp, vp, vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, i32, vp, vp, vp]
+    lib.dgr_densify_apply.restype = ctypes.c_int
+    lib.dgr_densify_apply.argtypes = [i32, ctypes.POINTER(DgrDensifyTensors), vp, vp, vp]
     lib.dgr_mark_visible.restype = ctypes.c_int
     lib.dgr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
     lib.dgr_debug_geom.restype = ctypes.c_int

@@ -3,8 +3,10 @@
 // without a CUDA device every compute entry point fails with an error string.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -12,6 +14,7 @@
 #include "dgr_backward.cuh"
 #include "dgr_binning.cuh"
 #include "dgr_collective.cuh"
+#include "dgr_densify.cuh"
 #include "dgr_knn.cuh"
 #include "dgr_fields.cuh"
 #include "dgr_optim.cuh"
@@ -100,7 +103,7 @@ int check_gaussians(const DgrSettings *s, const DgrGaussians *g) {
 constexpr size_t kMaxTileSmem = 200 * 1024;      // tile-histogram rows live in shared memory: up to 51200 tiles
 
 template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
-void launch_pre_fwd(const DgrSettings *s, const DgrGaussians *g, int *radii, char *geom, const GeomLayout &L, unsigned *colscan_done,
+void launch_pre_fwd(const DgrSettings *s, const DgrGaussians *g, int *radii, char *geom, const GeomLayout &L, unsigned *tile_count,
                     cudaStream_t st) {
     const size_t smem = (size_t)L.tiles * 4;
     if (smem > 48 * 1024)
@@ -109,7 +112,7 @@ void launch_pre_fwd(const DgrSettings *s, const DgrGaussians *g, int *radii, cha
         g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
         s->campos, g->means3D, g->shs, g->shs_rest, g->colors_precomp, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii,
         reinterpret_cast<Rec *>(geom + L.off_rec), reinterpret_cast<unsigned *>(geom + L.off_touched),
-        reinterpret_cast<unsigned *>(geom + L.off_blkhist), L.tiles, L.iters, colscan_done);
+        tile_count, L.tiles, L.iters);
 }
 
 template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
@@ -157,22 +160,58 @@ __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched
     if (tiles_touched) tiles_touched[g] = touched[g] & 0x1fffffffu;
 }
 
-bool g_sort_attr_set = false;
-int g_big_grid = 148;
-int g_snake = 1;
-int sm_count_raw() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
+// tuning knobs (dgr_set_tuning): pixels per lane of the render kernels, heaviest-first tile order on/off.  Atomics: any host
+// thread may change them while another launches (each launch reads every knob once).
+std::atomic<int> g_ppl_fwd{1}, g_ppl_bwd{2};
+std::atomic<bool> g_no_order{false};
+
+using SmS = SortSmem<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>;
+using SmB = SortSmem<kSortBigThreads, kSortBigCap, kSortBigBuckets>;
+
+// Per-DEVICE launch state: cudaFuncSetAttribute (dynamic shared memory above 48 KB) and the occupancy-derived persistent
+// grids are properties of a (function, device) pair, so they are kept per device ordinal and set up once under a mutex.
+struct DevInfo {
+    bool ready = false;
+    int sms = 148;
+    int fwd_grid[3] = {0, 0, 0};      // persistent grid of render_fwd_kernel<1|2|4>
+    int bwd_grid[2] = {0, 0};         // persistent grid of render_bwd_kernel<1|2>
+    int big_grid = 148;               // big-tile sorter: one CTA per SM
+};
+constexpr int kMaxDevices = 64;
+DevInfo g_dev[kMaxDevices];
+std::mutex g_dev_mu;
+
+template <class K>
+int persistent_grid(K kernel, int threads, size_t smem, int sms) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    return per_sm * sms;
 }
-int sm_count() { return g_snake ? sm_count_raw() : (1 << 30); }      // a huge "SM count" disables the snake order
-// tuning knobs (dgr_set_tuning): pixels per lane of the render kernels, heaviest-first tile order on/off
-int g_ppl_fwd = 1, g_ppl_bwd = 2, g_bwd_pair = 1;
-bool g_no_order = false;
-bool g_emit_attr_set = false;
+
+const DevInfo *dev_info() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { fail(-1, "cudaGetDevice failed or device ordinal above 63"); return nullptr; }
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    DevInfo &d = g_dev[dev];
+    if (d.ready) return &d;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) d.sms = n;
+    d.big_grid = d.sms;
+    cudaError_t e = cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sort_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmS::bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sort_gather_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmB::bytes);
+    const size_t b1 = sizeof(BwdSmem<1>) * kRenderWarps, b2 = sizeof(BwdSmem<2>) * kRenderWarps;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(render_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(render_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2);
+    if (e != cudaSuccess) { fail((int)e, "cudaFuncSetAttribute", cudaGetErrorString(e)); return nullptr; }
+    d.fwd_grid[0] = persistent_grid(render_fwd_kernel<1>, kRenderThreads, 0, d.sms);
+    d.fwd_grid[1] = persistent_grid(render_fwd_kernel<2>, kRenderThreads, 0, d.sms);
+    d.fwd_grid[2] = persistent_grid(render_fwd_kernel<4>, kRenderThreads, 0, d.sms);
+    d.bwd_grid[0] = persistent_grid(render_bwd_kernel<1>, kRenderThreads, b1, d.sms);
+    d.bwd_grid[1] = persistent_grid(render_bwd_kernel<2>, kRenderThreads, b2, d.sms);
+    d.ready = true;
+    return &d;
+}
 }  // namespace
 
 extern "C" {
@@ -206,8 +245,8 @@ int dgr_profile_collect(char *names, size_t names_bytes, float *ms, int max) {
 
 int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order) {
     if ((ppl_fwd != 1 && ppl_fwd != 2 && ppl_fwd != 4) || (ppl_bwd != 1 && ppl_bwd != 2 && ppl_bwd != 4)) return fail(-1, "ppl must be 1, 2 or 4");
-    g_ppl_fwd = ppl_fwd; g_ppl_bwd = ppl_bwd; g_bwd_pair = (tile_order & 4) == 0; tile_order &= 3;
-    g_no_order = tile_order == 0; g_snake = tile_order != 2;
+    g_ppl_fwd = ppl_fwd; g_ppl_bwd = ppl_bwd == 4 ? 2 : ppl_bwd;          // the backward has 8x4 and 8x8 sub-tiles
+    g_no_order = (tile_order & 3) == 0;
     return 0;
 }
 
@@ -232,13 +271,11 @@ int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *ge
     GeomLayout L(g->P, s->image_height, s->image_width);
     ImageLayout IL(s->image_height, s->image_width);
     if ((size_t)L.tiles * 4 > kMaxTileSmem) return fail(-3, "image has more than 51200 tiles (16x16): not supported");
-    TileWork *work = reinterpret_cast<TileWork *>(image + IL.off_work);
+    // one memset: the work block + the per-tile instance totals the preprocess kernel adds into
+    DGR_CUDA(cudaMemsetAsync(image + IL.off_work, 0, (IL.off_count - IL.off_work) + (size_t)L.tiles * 4, st));
     if (g->P > 0) {
         if (!radii) return fail(-1, "radii is NULL");
-        DGR_KERNEL("preprocess_fwd", st, s->debug, DGR_DISPATCH(launch_pre_fwd, s, g, radii, geom, L, &work->done, st));
-    } else {
-        DGR_CUDA(cudaMemsetAsync(geom + L.off_blkhist, 0, (size_t)L.nblocks * L.tiles * 4, st));
-        DGR_CUDA(cudaMemsetAsync(work, 0, sizeof(TileWork), st));
+        DGR_KERNEL("preprocess_fwd", st, s->debug, DGR_DISPATCH(launch_pre_fwd, s, g, radii, geom, L, reinterpret_cast<unsigned *>(image + IL.off_count), st));
     }
     return 0;
 }
@@ -261,7 +298,7 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
     if ((size_t)tiles * 4 > kMaxTileSmem) return fail(-3, "image has more than 51200 tiles (16x16): not supported");
     uint2 *ranges = reinterpret_cast<uint2 *>(image + IL.off_ranges);
     unsigned *tile_count = reinterpret_cast<unsigned *>(image + IL.off_count);
-    unsigned *blk_hist = reinterpret_cast<unsigned *>(geom + GL.off_blkhist);
+    unsigned *tile_cursor = reinterpret_cast<unsigned *>(image + IL.off_cursor);
     unsigned *n_contrib = reinterpret_cast<unsigned *>(image + IL.off_ncontrib);
     float *final_T = reinterpret_cast<float *>(image + IL.off_finalT);
     GeomHeader *hdr = reinterpret_cast<GeomHeader *>(geom);
@@ -273,44 +310,33 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
     unsigned *tile_order = reinterpret_cast<unsigned *>(image + IL.off_order);
     unsigned *big_list = reinterpret_cast<unsigned *>(image + IL.off_biglist);
     TileWork *work = reinterpret_cast<TileWork *>(image + IL.off_work);
-    if (flags & DGR_FLAG_RERUN)
-        DGR_KERNEL("tile_scan", st, s->debug,
-                   tile_scan_kernel<<<1, 1024, 0, st>>>(tiles, tile_count, (unsigned long long)capacity, ranges, hdr, tile_order, work, big_list, sm_count()));
-    else
-        DGR_KERNEL("tile_colscan_scan", st, s->debug,
-                   tile_colscan_kernel<<<(tiles + 31) / 32, 1024, 0, st>>>(tiles, GL.nblocks, blk_hist, tile_count, (unsigned long long)capacity,
-                                                                            ranges, hdr, tile_order, work, big_list, sm_count()));
+    const DevInfo *dv = dev_info();
+    if (!dv) return -1;
+    (void)(flags & DGR_FLAG_RERUN);           // a re-run only repeats the scan from the (still valid) per-tile totals
+    DGR_KERNEL("tile_scan", st, s->debug,
+               tile_scan_kernel<<<1, 1024, 0, st>>>(tiles, tile_count, (unsigned long long)capacity, ranges, tile_cursor, hdr, tile_order, work, big_list));
     if (counts_host)      // { n_instances, n_big_tiles }
         DGR_CUDA(cudaMemcpyAsync(counts_host, geom, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     if (count_ready_event) DGR_CUDA(cudaEventRecord((cudaEvent_t)count_ready_event, st));
     if (g->P > 0 && capacity > 0) {
         const size_t smem = (size_t)tiles * 4;
-        if (smem > 48 * 1024 && !g_emit_attr_set) {
-            DGR_CUDA(cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileSmem));
-            g_emit_attr_set = true;
-        }
         DGR_KERNEL("emit_instances", st, s->debug,
                    emit_instances_kernel<<<GL.nblocks, kPreThreads, smem, st>>>(
-                       g->P, IL.gx, tiles, GL.iters, rec, reinterpret_cast<const unsigned *>(geom + GL.off_touched), ranges, blk_hist, keys));
-        using SmS = SortSmem<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>;
-        using SmB = SortSmem<kSortBigThreads, kSortBigCap, kSortBigBuckets>;
-        if (!g_sort_attr_set) {
-            DGR_CUDA(cudaFuncSetAttribute(tile_sort_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmS::bytes));
-            DGR_CUDA(cudaFuncSetAttribute(tile_sort_gather_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmB::bytes));
-            g_sort_attr_set = true;
-        }
+                       g->P, IL.gx, tiles, GL.iters, rec, reinterpret_cast<const unsigned *>(geom + GL.off_touched), ranges, tile_cursor, keys));
         DGR_KERNEL("tile_sort_gather", st, s->debug,
                    tile_sort_gather_kernel<<<tiles, kSortSmallThreads, SmS::bytes, st>>>(tile_order, ranges, keys, rec, ids, recs));
         if (flags & DGR_FLAG_BIG_TILES)
             DGR_KERNEL("tile_sort_gather_big", st, s->debug,
-                       tile_sort_gather_big_kernel<<<g_big_grid, kSortBigThreads, SmB::bytes, st>>>(work, big_list, ranges, keys, rec, ids, recs));
+                       tile_sort_gather_big_kernel<<<dv->big_grid, kSortBigThreads, SmB::bytes, st>>>(work, big_list, ranges, keys, rec, ids, recs));
     }
-    const unsigned *render_order = g_no_order ? nullptr : tile_order;
-#define DGR_RENDER_FWD(PPL_)                                                                                   \
+    // persistent forward render: every (tile, sub-tile) is a work item, handed out heaviest tile first
+    const int ppl = g_ppl_fwd.load();
+#define DGR_RENDER_FWD(PPL_, GRID_)                                                                             \
     DGR_KERNEL("render_fwd", st, s->debug,                                                                      \
-               render_fwd_kernel<PPL_><<<(unsigned)tiles, SubTile<PPL_>::kThreads, 0, st>>>(                        \
-                   H, W, IL.gx, render_order, ranges, recs, s->bg, out->color, out->depth, out->alpha, n_contrib, final_T))
-    if (g_ppl_fwd == 4) DGR_RENDER_FWD(4); else if (g_ppl_fwd == 2) DGR_RENDER_FWD(2); else DGR_RENDER_FWD(1);
+               render_fwd_kernel<PPL_><<<(unsigned)min(GRID_, (tiles * SubTile<PPL_>::kPerTile + kRenderWarps - 1) / kRenderWarps), kRenderThreads, 0, st>>>(   \
+                   H, W, IL.gx, tile_order, (unsigned)(tiles * SubTile<PPL_>::kPerTile), &work->fwd_next, ranges, recs, s->bg,         \
+                   out->color, out->depth, out->alpha, n_contrib, final_T))
+    if (ppl == 4) DGR_RENDER_FWD(4, dv->fwd_grid[2]); else if (ppl == 2) DGR_RENDER_FWD(2, dv->fwd_grid[1]); else DGR_RENDER_FWD(1, dv->fwd_grid[0]);
 #undef DGR_RENDER_FWD
     return 0;
 }
@@ -333,42 +359,59 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
     BinningLayout BL(capacity);
     const int tiles = IL.gx * IL.gy;
     float *grad_rec = reinterpret_cast<float *>(geom + GL.off_gradrec);
-    DGR_CUDA(cudaMemsetAsync(grad_rec, 0, (size_t)g->P * kGradRecFloats * 4, st));
+    // one memset: the work counter of the persistent backward render kernel + the per-Gaussian moment accumulators
+    DGR_CUDA(cudaMemsetAsync(geom + GL.off_bwdwork, 0, (GL.off_gradrec - GL.off_bwdwork) + (size_t)g->P * kGradRecFloats * 4, st));
     if (binning && capacity > 0) {
-        const unsigned *tile_order = g_no_order ? nullptr : reinterpret_cast<const unsigned *>(image + IL.off_order);
-#define DGR_RENDER_BWD(PPL_, U2_)                                                                                              \
+        const DevInfo *dv = dev_info();
+        if (!dv) return -1;
+        const TileWork *work = reinterpret_cast<const TileWork *>(image + IL.off_work);
+        unsigned *bwd_next = reinterpret_cast<unsigned *>(geom + GL.off_bwdwork);
+        const int ppl = g_ppl_bwd.load();
+#define DGR_RENDER_BWD(PPL_, GRID_)                                                                                           \
     DGR_KERNEL("render_bwd", st, s->debug,                                                                                 \
-               render_bwd_kernel<PPL_, U2_><<<(unsigned)tiles, SubTile<PPL_>::kThreads, 0, st>>>(                                   \
-                   H, W, IL.gx, tile_order, reinterpret_cast<const uint2 *>(image + IL.off_ranges),                        \
+               render_bwd_kernel<PPL_><<<(unsigned)min(GRID_, (tiles * SubTile<PPL_>::kPerTile + kRenderWarps - 1) / kRenderWarps), kRenderThreads, \
+                                         sizeof(BwdSmem<PPL_>) * kRenderWarps, st>>>(                                          \
+                   H, W, IL.gx, reinterpret_cast<const unsigned *>(image + IL.off_order), &work->n_nonempty, bwd_next,     \
+                   reinterpret_cast<const uint2 *>(image + IL.off_ranges),                                                 \
                    reinterpret_cast<const Rec *>(binning + BL.off_rec), reinterpret_cast<const unsigned *>(binning + BL.off_ids), \
                    s->bg, reinterpret_cast<const float *>(image + IL.off_finalT),                                          \
                    reinterpret_cast<const unsigned *>(image + IL.off_ncontrib), gin->dL_dcolor, gin->dL_ddepth, gin->dL_dalpha, grad_rec))
-        if (g_bwd_pair) { if (g_ppl_bwd == 4) DGR_RENDER_BWD(4, true); else if (g_ppl_bwd == 2) DGR_RENDER_BWD(2, true); else DGR_RENDER_BWD(1, true); }
-        else { if (g_ppl_bwd == 4) DGR_RENDER_BWD(4, false); else if (g_ppl_bwd == 2) DGR_RENDER_BWD(2, false); else DGR_RENDER_BWD(1, false); }
+        if (ppl == 1) DGR_RENDER_BWD(1, dv->bwd_grid[0]); else DGR_RENDER_BWD(2, dv->bwd_grid[1]);
 #undef DGR_RENDER_BWD
     }
     DGR_KERNEL("preprocess_bwd", st, s->debug, DGR_DISPATCH(launch_pre_bwd, s, g, radii, reinterpret_cast<const unsigned *>(geom + GL.off_touched), grad_rec, gout, st));
     return 0;
 }
 
-int dgr_peer_allreduce(const uint64_t *peer_ptrs, int32_t world, int32_t rank, uint64_t n_floats, uint64_t multicast_ptr, void *stream) {
+size_t dgr_peer_flag_bytes(void) { return (size_t)2 * kMaxFlagBlocks * kMaxPeers * sizeof(unsigned); }
+
+int dgr_peer_allreduce(const uint64_t *peer_ptrs, int32_t world, int32_t rank, uint64_t n_floats, uint64_t multicast_ptr,
+                       const uint64_t *peer_flag_ptrs, uint32_t epoch, void *stream) {
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(-1, "bad world / rank");
     if (n_floats % 4 != 0) return fail(-1, "n_floats must be a multiple of 4");
     if (!peer_ptrs && !multicast_ptr) return fail(-1, "no peer pointers");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n4 = (size_t)(n_floats / 4);
     if (n4 == 0 || world == 1) return 0;
+    const DevInfo *dv = dev_info();
+    if (!dv) return -1;
     const size_t per = (n4 + world - 1) / world;
-    int grid = (int)((per + 511) / 512);
-    if (grid > 4 * sm_count_raw()) grid = 4 * sm_count_raw();
+    int grid = (int)((per + 512 * kUnroll - 1) / (512 * kUnroll));
+    if (grid > 4 * dv->sms) grid = 4 * dv->sms;
+    if (grid > kMaxFlagBlocks) grid = kMaxFlagBlocks;
     if (grid < 1) grid = 1;
+    PeerFlags pf;
+    for (int w = 0; w < kMaxPeers; w++) pf.p[w] = (peer_flag_ptrs && w < world) ? reinterpret_cast<unsigned *>(peer_flag_ptrs[w]) : nullptr;
+    const bool bar = peer_flag_ptrs != nullptr;
     if (multicast_ptr) {
-        DGR_KERNEL("allreduce_multimem", st, 0,
-                   allreduce_multimem_kernel<<<grid, 512, 0, st>>>(reinterpret_cast<float *>(multicast_ptr), world, rank, n4));
+        float *mc = reinterpret_cast<float *>(multicast_ptr);
+        if (bar) DGR_KERNEL("allreduce_multimem", st, 0, allreduce_multimem_kernel<true><<<grid, 512, 0, st>>>(mc, pf, epoch, world, rank, n4));
+        else DGR_KERNEL("allreduce_multimem", st, 0, allreduce_multimem_kernel<false><<<grid, 512, 0, st>>>(mc, pf, epoch, world, rank, n4));
     } else {
         PeerPtrs pp;
         for (int w = 0; w < kMaxPeers; w++) pp.p[w] = w < world ? reinterpret_cast<float *>(peer_ptrs[w]) : nullptr;
-        DGR_KERNEL("allreduce_p2p", st, 0, allreduce_p2p_kernel<<<grid, 512, 0, st>>>(pp, world, rank, n4));
+        if (bar) DGR_KERNEL("allreduce_p2p", st, 0, allreduce_p2p_kernel<true><<<grid, 512, 0, st>>>(pp, pf, epoch, world, rank, n4));
+        else DGR_KERNEL("allreduce_p2p", st, 0, allreduce_p2p_kernel<false><<<grid, 512, 0, st>>>(pp, pf, epoch, world, rank, n4));
     }
     return 0;
 }
@@ -393,7 +436,7 @@ int dgr_dist_cuda2(int32_t P, const float *points, float *mean_dists, void *scra
     DGR_CUDA(cudaMemsetAsync(cell_start, 0, (L.cap + 1) * 4, st));
     DGR_CUDA(cudaMemsetAsync(cell_fill, 0, L.cap * 4, st));
     const int nb = (P + 255) / 256;
-    const int nb_bbox = nb < 4 * sm_count_raw() ? nb : 4 * sm_count_raw();
+    const int nb_bbox = nb < 4 * (dev_info() ? dev_info()->sms : 148) ? nb : 4 * (dev_info() ? dev_info()->sms : 148);
     const size_t n_scan = L.cap + 1;
     DGR_KERNEL("knn_bbox", st, 0, knn_bbox_kernel<<<nb_bbox, 256, 0, st>>>(P, points, grid));
     DGR_KERNEL("knn_grid", st, 0, knn_grid_kernel<<<1, 1, 0, st>>>(P, (unsigned)L.cap, grid));
@@ -432,7 +475,7 @@ int dgr_extract_fields(int32_t P, const float *xyz, const float *opacity_raw, co
     DGR_CUDA(cudaMemsetAsync(cell_fill, 0, L.cells * 4, st));
     const int nbk = P > 0 ? (P + 255) / 256 : 1;
     if (P > 0) {
-        const int nb_bbox = nbk < 4 * sm_count_raw() ? nbk : 4 * sm_count_raw();
+        const int nb_bbox = nbk < 4 * (dev_info() ? dev_info()->sms : 148) ? nbk : 4 * (dev_info() ? dev_info()->sms : 148);
         DGR_KERNEL("fields_bbox", st, 0, fields_bbox_kernel<<<nb_bbox, 256, 0, st>>>(P, xyz, opacity_raw, hdr));
     }
     DGR_KERNEL("fields_prep", st, 0, fields_prep_kernel<<<nbk, 256, 0, st>>>(P, xyz, opacity_raw, scaling_raw, rotation_raw, hdr, num_blocks,
@@ -470,9 +513,55 @@ int dgr_adam_step(const DgrAdamGroup *groups, int32_t n_groups, double beta1, do
     if (run == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long blocks = (run + 255) / 256;
-    const unsigned long long cap = (unsigned long long)sm_count_raw() * 16;
+    const unsigned long long cap = (unsigned long long)(dev_info() ? dev_info()->sms : 148) * 16;
     if (blocks > cap) blocks = cap;
     DGR_KERNEL("adam_multi", st, 0, adam_multi_kernel<<<(unsigned)blocks, 256, 0, st>>>(G, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps));
+    return 0;
+}
+
+size_t dgr_densify_scratch_bytes(int32_t P) { return DensifyLayout(P).total; }
+
+int dgr_densify_plan(int32_t P, const float *xyz_gradient_accum, const float *denom, const float *opacity_raw, const float *scaling_raw,
+                     float grad_threshold, float dense_extent, float min_opacity, float max_world, int32_t use_world,
+                     void *scratch_v, uint32_t *counts_host, void *stream) {
+    if (P < 0) return fail(-1, "P < 0");
+    if (!scratch_v || (P > 0 && (!xyz_gradient_accum || !denom || !opacity_raw || !scaling_raw))) return fail(-1, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    char *scratch = (char *)scratch_v;
+    DensifyLayout L(P);
+    unsigned *counts = reinterpret_cast<unsigned *>(scratch + L.off_counts), *offsets = reinterpret_cast<unsigned *>(scratch + L.off_offsets);
+    unsigned *totals = reinterpret_cast<unsigned *>(scratch + L.off_totals);
+    DensifyParams prm{grad_threshold, dense_extent, min_opacity, max_world, use_world};
+    if (P > 0)
+        DGR_KERNEL("densify_classify", st, 0,
+                   densify_classify_kernel<<<L.nblk, kDensifyThreads, 0, st>>>(P, xyz_gradient_accum, denom, opacity_raw, scaling_raw, prm,
+                                                                                reinterpret_cast<unsigned char *>(scratch + L.off_class), counts));
+    else
+        DGR_CUDA(cudaMemsetAsync(counts, 0, 16, st));
+    DGR_KERNEL("densify_offsets", st, 0, densify_offsets_kernel<<<1, 1024, 0, st>>>(P > 0 ? L.nblk : 1, counts, offsets, totals));
+    if (counts_host) DGR_CUDA(cudaMemcpyAsync(counts_host, totals, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int dgr_densify_apply(int32_t P, const DgrDensifyTensors *t, const float *noise, const void *scratch_v, void *stream) {
+    if (P < 0 || !t || !scratch_v) return fail(-1, "bad argument");
+    if (P == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const char *scratch = (const char *)scratch_v;
+    DensifyLayout L(P);
+    DensifyTensors T;
+    for (int k = 0; k < kDensifyTensors; k++) {
+        T.in[k] = t->in[k]; T.m_in[k] = t->exp_avg_in[k]; T.v_in[k] = t->exp_avg_sq_in[k];
+        T.out[k] = t->out[k]; T.m_out[k] = t->exp_avg_out[k]; T.v_out[k] = t->exp_avg_sq_out[k];
+        T.width[k] = t->width[k];
+        if (t->width[k] < 0) return fail(-1, "negative row width");
+        if (t->width[k] > 0 && (!T.in[k] || !T.m_in[k] || !T.v_in[k])) return fail(-1, "NULL input tensor");
+    }
+    if (T.width[0] != 3 || T.width[3] != 1 || T.width[4] != 3 || T.width[5] != 4) return fail(-1, "row widths must be xyz 3, opacity 1, scaling 3, rotation 4");
+    DGR_KERNEL("densify_apply", st, 0,
+               densify_apply_kernel<<<L.nblk, kDensifyThreads, 0, st>>>(P, reinterpret_cast<const unsigned char *>(scratch + L.off_class),
+                                                                        reinterpret_cast<const unsigned *>(scratch + L.off_offsets),
+                                                                        reinterpret_cast<const unsigned *>(scratch + L.off_totals), T, noise));
     return 0;
 }
 

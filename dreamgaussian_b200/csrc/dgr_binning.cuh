@@ -1,18 +1,17 @@
-// dgr_binning.cuh — tile binning (A3 of SURVEY.md §8a) without a global sort and without global atomics.
+// dgr_binning.cuh — tile binning (A3 of SURVEY.md §8a) without a global sort.
 //
 // The reference op sorts ALL (tile, depth) keys with one device-wide 64-bit radix sort (6 passes over N_inst pairs)
 // and reads the instance count back to the host.  Here:
-//   1. the preprocess kernel histograms the instances of each block of Gaussians per tile in shared memory and writes
-//      one row of a [blocks x tiles] count matrix;
-//   2. tile_colscan_kernel turns every column into exclusive per-(block, tile) offsets and the per-tile totals,
-//      tile_scan_kernel turns the totals into per-tile [start, end) ranges (clipped to the buffer capacity) and
-//      publishes the instance count — all on the device, no host round trip is needed to continue;
-//   3. emit_instances_kernel (same block <-> Gaussian mapping) loads its matrix row into shared memory and appends
-//      (depth bits << 32 | Gaussian id) keys at range.start + offset[block][tile] + local rank (shared-memory atomics);
-//   4. tile_sort_gather_kernel sorts each tile's segment by (depth, id) in shared memory (bitonic network; keys are
-//      unique, so the result is deterministic and identical to the reference's stable (tile, depth) order) and, in the
-//      same pass, gathers the 48-byte records into depth-sorted, per-tile contiguous order for the bulk-TMA staging
-//      of the render kernels.
+//   1. the preprocess kernel histograms the instances of each block of Gaussians per tile in shared memory and adds the
+//      block's counts to the per-tile totals (one global atomic per touched (block, tile), not per instance);
+//   2. tile_scan_kernel turns the totals into per-tile [start, end) ranges (clipped to the buffer capacity), publishes the
+//      instance count, the heaviest-first issue order and the big-tile list — all on the device, no host round trip;
+//   3. emit_instances_kernel counts its block's instances per tile again (shared memory), reserves a contiguous run of
+//      each touched tile's range with ONE global atomic, and appends (depth bits << 32 | Gaussian id) keys there with
+//      shared-memory cursors.  The order inside a tile is arbitrary at this point;
+//   4. tile_sort_gather_kernel sorts each tile's segment by (depth, id) in shared memory (keys are unique, so the result
+//      is deterministic and identical to the reference's stable (tile, depth) order) and, in the same pass, gathers the
+//      48-byte records into depth-sorted, per-tile contiguous order for the bulk-TMA staging of the render kernels.
 #pragma once
 #include "dgr_common.cuh"
 
@@ -67,8 +66,9 @@ constexpr int kOrderBins = 128;          // log-scale population classes for the
 
 struct TileWork {                        // lives in image scratch
     unsigned n_big;                      // number of entries of big_list (written by the tile scan)
-    unsigned done;                       // CTAs of tile_colscan_kernel that have finished (zeroed by the preprocess kernel)
-    unsigned pad[2];
+    unsigned reserved;
+    unsigned n_nonempty;                 // tiles with at least one instance = the leading entries of tile_order
+    unsigned fwd_next;                   // work counter of the persistent forward render kernel (zeroed by the tile scan)
 };
 
 __device__ __forceinline__ int order_bin(unsigned count) {
@@ -89,13 +89,13 @@ constexpr int kScanTPT = 8;
 
 __device__ __forceinline__ void
 tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long long cap, uint2 *__restrict__ ranges,
-              GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order, TileWork *__restrict__ work,
-              unsigned *__restrict__ big_list, int nsm) {
+              unsigned *__restrict__ tile_cursor, GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order,
+              TileWork *__restrict__ work, unsigned *__restrict__ big_list) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_carry, s_total;
-    __shared__ unsigned s_bin[kOrderBins], s_nbig;
+    __shared__ unsigned s_bin[kOrderBins], s_nbig, s_nne;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_carry = 0; s_nbig = 0; }
+    if (tid == 0) { s_carry = 0; s_nbig = 0; s_nne = 0; }
     if (tid < kOrderBins) s_bin[tid] = 0;
     __syncthreads();
     const int span = 1024 * kScanTPT;
@@ -126,9 +126,11 @@ tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
                 const unsigned long long s = run < cap ? run : cap;
                 const unsigned long long e = (run + cnt[j]) < cap ? (run + cnt[j]) : cap;
                 ranges[t0 + j] = make_uint2((unsigned)s, (unsigned)e);
+                tile_cursor[t0 + j] = (unsigned)s;                            // emit reserves runs of the range from here
                 const unsigned pop = (unsigned)(e - s);                       // clipped population
                 atomicAdd(&s_bin[order_bin(pop)], 1u);
                 if (pop > (unsigned)kSortSmallCap) big_list[atomicAdd(&s_nbig, 1u)] = (unsigned)(t0 + j);
+                if (pop > 0u) atomicAdd(&s_nne, 1u);
             }
             run += cnt[j];
         }
@@ -136,7 +138,7 @@ tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
         if (tid == 0) s_carry += s_total;
         __syncthreads();
     }
-    if (tid == 0) { hdr->n_inst = s_carry; hdr->n_big = s_nbig; work->n_big = s_nbig; }
+    if (tid == 0) { hdr->n_inst = s_carry; hdr->n_big = s_nbig; work->n_big = s_nbig; work->n_nonempty = s_nne; work->fwd_next = 0u; }
     // counting sort of the tiles by population class (heaviest first)
     if (warp == 0) {
         unsigned run = 0;
@@ -150,108 +152,67 @@ tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
         }
     }
     __syncthreads();
-    // The block scheduler deals the first CTAs round-robin over the SMs (CTA i -> SM i mod nsm), so a plainly descending
-    // order would hand SM 0 the heaviest tile of EVERY round.  Reversing every other round of nsm ("snake" order) gives
-    // each SM one heavy and one light tile per pair of rounds: measured 25% less spread of SM busy time.
-    const int full = (tiles / nsm) * nsm;
+    // Plain descending order: the render kernels are persistent and pull work items from this list through an atomic
+    // counter (longest processing time first); the empty tiles form its tail (class kOrderBins - 1).
     for (int t = tid; t < tiles; t += 1024) {
         const uint2 r = ranges[t];
-        int pos = (int)atomicAdd(&s_bin[order_bin(r.y - r.x)], 1u);
-        if (pos < full) { const int k = pos / nsm, i = pos - k * nsm; pos = k * nsm + ((k & 1) ? (nsm - 1 - i) : i); }
+        const int pos = (int)atomicAdd(&s_bin[order_bin(r.y - r.x)], 1u);
         tile_order[pos] = (unsigned)t;
     }
 }
 
-// Stand-alone tile scan: used when stage 2 is re-run with a larger capacity (the column scan must not run twice: it
-// rewrote the count matrix in place; the column totals in tile_count are still valid).
+// One CTA.  (Re-run with a larger capacity when the caller's guess was too small: the totals in tile_count stay valid.)
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int tiles, const unsigned *__restrict__ tile_count, unsigned long long cap, uint2 *__restrict__ ranges,
-                 GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order, TileWork *__restrict__ work,
-                 unsigned *__restrict__ big_list, int nsm) {
-    tile_scan_cta(tiles, tile_count, cap, ranges, hdr, tile_order, work, big_list, nsm);
+                 unsigned *__restrict__ tile_cursor, GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order,
+                 TileWork *__restrict__ work, unsigned *__restrict__ big_list) {
+    tile_scan_cta(tiles, tile_count, cap, ranges, tile_cursor, hdr, tile_order, work, big_list);
 }
 
-// Column scan of the [nblocks x tiles] count matrix (in place -> exclusive per-(block, tile) offsets) + column totals.
-// One CTA = 32 tiles (lanes, coalesced 128-byte rows) x 32 block-groups (warps): every thread first sums its slice of
-// the column, the 32 partial sums are scanned through shared memory, then the slice is rewritten as running offsets.
-__global__ void __launch_bounds__(1024)
-tile_colscan_kernel(int tiles, int nblocks, unsigned *__restrict__ blk_hist, unsigned *__restrict__ tile_count,
-                    unsigned long long cap, uint2 *__restrict__ ranges, GeomHeader *__restrict__ hdr,
-                    unsigned *__restrict__ tile_order, TileWork *__restrict__ work, unsigned *__restrict__ big_list, int nsm) {
-    __shared__ unsigned s_part[32][33];
-    __shared__ unsigned s_ticket;
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const int t = blockIdx.x * 32 + lane;
-    const int per = (nblocks + 31) / 32;
-    const int b0 = grp * per, b1 = min(nblocks, b0 + per);
-    constexpr int kRegRows = 16;                    // slices of up to 16 rows stay in registers: the matrix is read once
-    unsigned v[kRegRows];
-    unsigned sum = 0;
-    const bool in_regs = per <= kRegRows;
-    if (t < tiles) {
-        const unsigned *p = blk_hist + t;
-        if (in_regs) {
-#pragma unroll
-            for (int j = 0; j < kRegRows; j++) { v[j] = (b0 + j < b1) ? p[(size_t)(b0 + j) * tiles] : 0u; }
-#pragma unroll
-            for (int j = 0; j < kRegRows; j++) sum += v[j];
-        } else {
-#pragma unroll 4
-            for (int b = b0; b < b1; b++) sum += p[(size_t)b * tiles];
-        }
-    }
-    s_part[grp][lane] = sum;
-    __syncthreads();
-    if (grp == 0) {                       // one warp: exclusive scan over the 32 groups of each tile (lane = tile)
-        unsigned run = 0;
-#pragma unroll
-        for (int g = 0; g < 32; g++) { const unsigned x = s_part[g][lane]; s_part[g][lane] = run; run += x; }
-        if (t < tiles) tile_count[t] = run;
-    }
-    __syncthreads();
-    if (t < tiles) {
-        unsigned run = s_part[grp][lane];
-        unsigned *p = blk_hist + t;
-        if (in_regs) {
-#pragma unroll
-            for (int j = 0; j < kRegRows; j++) { if (b0 + j < b1) p[(size_t)(b0 + j) * tiles] = run; run += v[j]; }
-        } else {
-#pragma unroll 4
-            for (int b = b0; b < b1; b++) { const unsigned c = p[(size_t)b * tiles]; p[(size_t)b * tiles] = run; run += c; }
-        }
-    }
-    // the last CTA to finish turns the column totals into tile ranges (saves a launch and its round trip)
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&work->done, 1u);
-    __syncthreads();
-    if (s_ticket == gridDim.x - 1) {
-        __threadfence();
-        tile_scan_cta(tiles, tile_count, cap, ranges, hdr, tile_order, work, big_list, nsm);
-        if (threadIdx.x == 0) work->done = 0u;          // ready for a re-run of stage 2 with a larger capacity
-    }
-}
-
-// Same block <-> Gaussian mapping as the preprocess kernel.  s_off[t] = ranges[t].start + offset[block][t];
-// every instance takes the next slot of its tile with a shared-memory atomic.
+// Same block <-> Gaussian mapping as the preprocess kernel.  Pass 1 counts the block's instances per tile in shared
+// memory; every touched tile then reserves a contiguous run [base, base + count) of its range with one global atomic on
+// the tile's cursor; pass 2 appends the keys at base + (shared-memory atomic rank).  Runs beyond the (capacity-clipped)
+// range end are dropped.
 __global__ void __launch_bounds__(kPreThreads)
 emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, const Rec *__restrict__ rec, const unsigned *__restrict__ touched,
-                      const uint2 *__restrict__ ranges, const unsigned *__restrict__ blk_off,
+                      const uint2 *__restrict__ ranges, unsigned *__restrict__ tile_cursor,
                       unsigned long long *__restrict__ keys) {
     extern __shared__ unsigned s_off[];
-    const unsigned *row = blk_off + (size_t)blockIdx.x * tiles;
-    for (int t = threadIdx.x; t < tiles; t += kPreThreads) s_off[t] = ranges[t].x + row[t];
+    for (int t = threadIdx.x; t < tiles; t += kPreThreads) s_off[t] = 0u;
     __syncthreads();
+    // pass 1: per-tile counts of this block (the same AABB walk as the preprocess histogram)
     for (int it = 0; it < gpb_iters; it++) {
         const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + threadIdx.x);
         if (g >= P) continue;
-        if ((touched[g] & 0x1fffffffu) == 0) continue;
-        const float4 q1 = rec[g].q1;
-        const unsigned long long key = ((unsigned long long)__float_as_uint(q1.z) << 32) | (unsigned)g;
-        const unsigned ax = __float_as_uint(q1.w), ay = __float_as_uint(rec[g].q2.w);
+        const int cnt = (int)(__ldg(touched + g) & 0x1fffffffu);
+        if (cnt == 0) continue;
+        const unsigned ax = __float_as_uint(__ldg(&rec[g].q1.w)), ay = __float_as_uint(__ldg(&rec[g].q2.w));
         const int tx0 = (int)(ax & 0xffffu) >> 4, tw = ((int)(ax >> 16) >> 4) - tx0 + 1;
         const int ty0 = (int)(ay & 0xffffu) >> 4;
-        const int cnt = (int)(touched[g] & 0x1fffffffu);                  // = tw * th (same AABB as the histogram)
+        int x = 0, t = ty0 * gx + tx0;
+        for (int i = 0; i < cnt; i++) {
+            atomicAdd(&s_off[t], 1u);
+            x++; t++;
+            if (x == tw) { x = 0; t += gx - tw; }
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < tiles; t += kPreThreads) {
+        const unsigned c = s_off[t];
+        if (c) s_off[t] = atomicAdd(tile_cursor + t, c);
+    }
+    __syncthreads();
+    // pass 2: append
+    for (int it = 0; it < gpb_iters; it++) {
+        const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + threadIdx.x);
+        if (g >= P) continue;
+        const int cnt = (int)(__ldg(touched + g) & 0x1fffffffu);                  // = tw * th (same AABB as the histogram)
+        if (cnt == 0) continue;
+        const float4 q1 = __ldg(&rec[g].q1);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(q1.z) << 32) | (unsigned)g;
+        const unsigned ax = __float_as_uint(q1.w), ay = __float_as_uint(__ldg(&rec[g].q2.w));
+        const int tx0 = (int)(ax & 0xffffu) >> 4, tw = ((int)(ax >> 16) >> 4) - tx0 + 1;
+        const int ty0 = (int)(ay & 0xffffu) >> 4;
         int x = 0, t = ty0 * gx + tx0;
 #pragma unroll 4
         for (int i = 0; i < cnt; i++) {
@@ -367,6 +328,7 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
     }
     __syncthreads();
     // rank inside the bucket with the full key, write id + record to the final position
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     for (int i = tid; i < n; i += THREADS) {
         const unsigned long long k = B[i];
         const float d = __uint_as_float((unsigned)(k >> 32));
@@ -378,8 +340,9 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
         const size_t pos = (size_t)r.x + s + rank;
         ids_sorted[pos] = gid;
         const Rec *src = rec + gid;
-        Rec v; v.q0 = __ldg(&src->q0); v.q1 = __ldg(&src->q1); v.q2 = __ldg(&src->q2);
-        rec_sorted[pos] = v;
+        const float4 g0 = ldg_f4_hint(&src->q0, pol_keep), g1 = ldg_f4_hint(&src->q1, pol_keep), g2 = ldg_f4_hint(&src->q2, pol_keep);
+        Rec *dst = rec_sorted + pos;
+        stg_f4_hint(&dst->q0, g0, pol_stream); stg_f4_hint(&dst->q1, g1, pol_stream); stg_f4_hint(&dst->q2, g2, pol_stream);
     }
     __syncthreads();
 }

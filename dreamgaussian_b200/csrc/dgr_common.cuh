@@ -43,20 +43,21 @@ static_assert(sizeof(GeomHeader) == 64, "GeomHeader");
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Gaussians per block of the preprocess / emit kernels = kPreThreads * iters; iters grows so that the
-// [blocks x tiles] count matrix stays below 64 MB.
+// Gaussians per block of the preprocess / emit kernels = kPreThreads * iters.  Every block keeps a per-tile histogram in
+// shared memory and publishes it with one global atomic per touched tile, so a few thousand Gaussians per block keep that
+// traffic small for big clouds while small clouds still spread over all SMs (about 4 blocks per SM at least).
 __host__ __device__ inline int choose_gpb_iters(int P, int tiles) {
-    const size_t blocks1 = ((size_t)(P > 0 ? P : 1) + kPreThreads - 1) / kPreThreads;
-    const size_t bytes = blocks1 * (size_t)(tiles > 0 ? tiles : 1) * 4;
-    size_t k = (bytes + ((size_t)64 << 20) - 1) / ((size_t)64 << 20);
+    (void)tiles;
+    long long k = (long long)(P > 0 ? P : 1) / ((long long)kPreThreads * 600);
     if (k < 1) k = 1;
-    if (k > 64) k = 64;
+    if (k > 16) k = 16;
     return (int)k;
 }
 
-// geom scratch: [header 256][rec 48 x P][touched u32 x P][moments 48 x P (backward)][count matrix u32 x blocks x tiles]
+// geom scratch: [header 256][rec 48 x P][touched u32 x P][backward work counter 256][moments 48 x P (backward)]
+//               (the backward zeroes counter + moments with ONE memset)
 struct GeomLayout {
-    size_t off_rec, off_touched, off_gradrec, off_blkhist, total;
+    size_t off_rec, off_touched, off_bwdwork, off_gradrec, total;
     int tiles, iters, nblocks;
     __host__ __device__ GeomLayout(int P, int H, int W) {
         size_t Pn = P > 0 ? (size_t)P : 1;
@@ -67,27 +68,29 @@ struct GeomLayout {
         size_t o = 256;
         off_rec = o;     o = align_up(o + Pn * sizeof(Rec), 256);
         off_touched = o; o = align_up(o + Pn * 4, 256);
+        off_bwdwork = o; o += 256;
         off_gradrec = o; o = align_up(o + Pn * kGradRecFloats * 4, 256);
-        off_blkhist = o; o = align_up(o + (size_t)nblocks * tiles * 4, 256);
         total = o;
     }
 };
 
-// image scratch: [ranges uint2 x tiles][tile_count u32 x tiles][tile_order u32 x tiles][big_list u32 x tiles][work 256]
-//                [n_contrib u32 x HW][final_T f32 x HW]
+// image scratch: [work 256][tile_count u32 x tiles][ranges uint2 x tiles][tile_cursor u32 x tiles][tile_order u32 x tiles]
+//                [big_list u32 x tiles][n_contrib u32 x HW][final_T f32 x HW]
+// (work + tile_count are adjacent: the forward zeroes both with ONE memset before the preprocess kernel adds into tile_count)
 struct ImageLayout {
-    size_t off_ranges, off_count, off_order, off_biglist, off_work, off_ncontrib, off_finalT, total;
+    size_t off_ranges, off_count, off_cursor, off_order, off_biglist, off_work, off_ncontrib, off_finalT, total;
     int gx, gy;
     __host__ __device__ ImageLayout(int H, int W) {
         gx = (W + kTile - 1) / kTile; gy = (H + kTile - 1) / kTile;
         size_t tiles = (size_t)gx * gy; if (tiles < 1) tiles = 1;
         size_t hw = (size_t)H * W; if (hw < 1) hw = 1;
         size_t o = 0;
-        off_ranges = o;   o = align_up(o + tiles * 8, 256);
+        off_work = o;     o = align_up(o + 256, 256);
         off_count = o;    o = align_up(o + tiles * 4, 256);
+        off_ranges = o;   o = align_up(o + tiles * 8, 256);
+        off_cursor = o;   o = align_up(o + tiles * 4, 256);
         off_order = o;    o = align_up(o + tiles * 4, 256);
         off_biglist = o;  o = align_up(o + tiles * 4, 256);
-        off_work = o;     o = align_up(o + 256, 256);
         off_ncontrib = o; o = align_up(o + hw * 4, 256);
         off_finalT = o;   o = align_up(o + hw * 4, 256);
         total = o;
@@ -137,6 +140,22 @@ __device__ __forceinline__ void red_add_f32(float *addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ float4 ldg_f4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+// L2 residency control for the record gather of the per-tile sort: the per-Gaussian record array (48 B x P) is re-read N/P
+// times at random and should stay in L2, the sorted copy (48 B x N) is written once and read once by the render kernels.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float4 *p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg_f4_hint(float4 *p, const float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
 __device__ __forceinline__ float lg2_approx(float x) {
     float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }

@@ -1,6 +1,7 @@
 // dgr_preprocess.cuh — per-Gaussian forward kernel (A2 of SURVEY.md §8a): frustum cull, cov3D, EWA cov2D, conic,
 // radius, pixel mean, SH -> RGB, opacity-aware pixel AABB, and — fused — a per-block tile histogram (shared-memory
-// atomics, one matrix row per block) that replaces the reference's per-Gaussian prefix sum + host read-back.
+// atomics, published with one global atomic per touched tile) that replaces the reference's per-Gaussian prefix sum +
+// host read-back.
 // Streaming, HBM-bound: reads 44 + 12 M bytes, writes 56 bytes per Gaussian.
 //
 // Reference behaviour restated (not copied): the `preprocessCUDA` step of the op called at
@@ -155,14 +156,13 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                       const float *__restrict__ scales, const float *__restrict__ rotations,
                       const float *__restrict__ cov3D_precomp,
                       int *__restrict__ radii, Rec *__restrict__ rec, unsigned *__restrict__ touched_out,
-                      unsigned *__restrict__ blk_hist, int tiles, int gpb_iters, unsigned *__restrict__ colscan_done) {
-    // Per-block tile histogram in shared memory (native integer smem atomics, no global atomics): row `blockIdx.x` of
-    // the [blocks x tiles] matrix that tile_colscan_kernel turns into per-(block, tile) offsets.
+                      unsigned *__restrict__ tile_count, int tiles, int gpb_iters) {
+    // Per-block tile histogram in shared memory (native integer smem atomics); at the end every touched tile's count is
+    // added to the per-tile totals with ONE global atomic per (block, tile) — not one per instance.
     extern __shared__ unsigned s_hist[];
     __shared__ FrameConsts fc;
     load_frame(fc, viewmatrix, projmatrix, HAS_SH ? campos : nullptr);
     for (int t = threadIdx.x; t < tiles; t += kPreThreads) s_hist[t] = 0u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *colscan_done = 0u;      // completion counter of the column-scan kernel
     __syncthreads();
     for (int it = 0; it < gpb_iters; it++) {
     const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + threadIdx.x);
@@ -251,7 +251,7 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                     r.q0 = make_float4(mx, my, cA * (-0.5f * kLog2e), cB * (-kLog2e));
                     r.q1 = make_float4(cC * (-0.5f * kLog2e), o, geo.t[2], __uint_as_float((unsigned)bx0 | ((unsigned)bx1 << 16)));
                     r.q2 = make_float4(cr, cg, cb, __uint_as_float((unsigned)by0 | ((unsigned)by1 << 16)));
-                    // per-tile instance histogram of this block (tile_colscan_kernel turns the rows into offsets)
+                    // per-tile instance histogram of this block
                     for_each_touched_tile(__float_as_uint(r.q1.w), __float_as_uint(r.q2.w), gx,
                                           [&](int t) { atomicAdd(&s_hist[t], 1u); touched++; });
                 }
@@ -263,8 +263,10 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
     }
     }
     __syncthreads();
-    unsigned *row = blk_hist + (size_t)blockIdx.x * tiles;
-    for (int t = threadIdx.x; t < tiles; t += kPreThreads) row[t] = s_hist[t];
+    for (int t = threadIdx.x; t < tiles; t += kPreThreads) {
+        const unsigned c = s_hist[t];
+        if (c) atomicAdd(tile_count + t, c);            // result unused -> RED
+    }
 }
 
 __global__ void mark_visible_kernel(int P, const float *__restrict__ means3D, const float *__restrict__ V, unsigned char *present) {

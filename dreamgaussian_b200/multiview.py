@@ -23,7 +23,7 @@ class FlatGrads:
     symmetric=True allocates it in symmetric (peer-mapped) memory so the ranks can reduce it with the library's own
     NVLink kernel; the buffer is padded to a multiple of 64 floats so it splits into float4 slices for any world size."""
 
-    def __init__(self, P: int, M: int, device, with_means2D: bool = True, symmetric: bool = False):
+    def __init__(self, P: int, M: int, device, with_means2D: bool = True, symmetric: bool = False, flag_floats: int = 0):
         self.P, self.M = P, M
         sizes = [("means3D", 3 * P, (P, 3)), ("shs", 3 * M * P, (P, M, 3)), ("opacities", P, (P, 1)),
                  ("scales", 3 * P, (P, 3)), ("rotations", 4 * P, (P, 4))]
@@ -32,12 +32,15 @@ class FlatGrads:
         total = sum(n for _, n, _ in sizes)
         self.numel = total
         padded = (total + 63) // 64 * 64
+        self.padded = padded
         if symmetric:
             import torch.distributed._symmetric_memory as symm_mem
-            self.storage = symm_mem.empty(padded, dtype=torch.float32, device=device)
+            # [gradient data | cross-rank barrier flags of the all-reduce kernel]: one symmetric allocation, one rendezvous
+            self.storage = symm_mem.empty(padded + flag_floats, dtype=torch.float32, device=device)
             self.storage.zero_()
         else:
             self.storage = torch.zeros((padded,), dtype=torch.float32, device=device)
+        self.data = self.storage[:padded]                 # what the all-reduce covers
         self.flat = self.storage[:total]
         self.views = {}
         o = 0
@@ -68,12 +71,19 @@ class ViewShardedRasterizer:
             # the gradient buffer in symmetric memory + this library's NVLink all-reduce kernel; NCCL is the fallback
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                self.grads = FlatGrads(P, M, self.device, symmetric=True)
+                from . import _lib
+                flag_floats = int(_lib.load().dgr_peer_flag_bytes()) // 4
+                self.grads = FlatGrads(P, M, self.device, symmetric=True, flag_floats=flag_floats)
                 group = process_group if process_group is not None else dist.group.WORLD
                 self._hdl = symm_mem.rendezvous(self.grads.storage, group)
                 mc = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
                 self._mc = mc if (mc and os.environ.get("DGR_NO_MULTIMEM") != "1") else 0
                 self._ptrs = (ctypes.c_uint64 * len(self._hdl.buffer_ptrs))(*[int(p) for p in self._hdl.buffer_ptrs])
+                # the flag area follows the gradient data in every rank's copy; in-kernel barriers unless DGR_HOST_BARRIERS=1
+                self._flags = (ctypes.c_uint64 * len(self._hdl.buffer_ptrs))(*[int(p) + 4 * self.grads.padded for p in self._hdl.buffer_ptrs])
+                self._inkernel = os.environ.get("DGR_HOST_BARRIERS") != "1"
+                self._epoch = 0
+                self._hdl.barrier(channel=0)              # every rank has zeroed its flags before anyone signals
                 self.collective = "own kernel: multimem (NVLS)" if self._mc else "own kernel: p2p two-shot"
                 if self._mc and os.environ.get("DGR_FORCE_MULTIMEM") != "1":
                     self._autotune(group)
@@ -101,8 +111,8 @@ class ViewShardedRasterizer:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
             if best is None or float(t) < best[0]:
                 best = (float(t), cand, name)
-        self._mc, self.collective = best[1], best[2] + " (auto-tuned, %.0f us)" % (best[0] * 1e3)
-        self.grads.storage.zero_()
+        self._mc, self.collective = best[1], best[2] + " (auto-tuned, %.0f us%s)" % (best[0] * 1e3, ", barriers inside the kernel" if self._inkernel else "")
+        self.grads.data.zero_()
 
     def render_views(self, params: dict, settings: Sequence[_r.GaussianRasterizationSettings],
                      upstream: Sequence[tuple], keep_images: bool = False):
@@ -112,7 +122,7 @@ class ViewShardedRasterizer:
         if len(settings) == 0:
             # a rank without a view this iteration (fewer views than ranks) contributes ZERO to the all-reduce; without this
             # its buffer would still hold the previous iteration's reduced sum
-            self.grads.storage.zero_()
+            self.grads.data.zero_()
         for i, (rs, up) in enumerate(zip(settings, upstream)):
             color, radii, depth, alpha, state = _r.forward_impl(
                 rs, params["means3D"], params["shs"], None, params["opacities"], params["scales"], params["rotations"], None)
@@ -123,20 +133,25 @@ class ViewShardedRasterizer:
         return images
 
     def all_reduce(self):
-        """Sum the flat gradient over ranks: this library's NVLink kernel on the symmetric buffer (two device-side
-        cross-rank barriers around it), else NCCL (gloo in the CPU tests of the host logic)."""
+        """Sum the flat gradient over ranks: this library's NVLink kernel on the symmetric buffer (its two cross-rank
+        barriers are inside the kernel), else NCCL (gloo in the CPU tests of the host logic)."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1):
             return self.grads.flat
         if self._hdl is not None:
             from . import _lib
             lib = _lib.load()
-            self._hdl.barrier(channel=0)
+            self._epoch += 1
+            if not self._inkernel:
+                self._hdl.barrier(channel=0)
             with torch.cuda.device(self.device):
                 st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+                flags = ctypes.cast(self._flags, ctypes.c_void_p) if self._inkernel else None
                 _lib.check(lib.dgr_peer_allreduce(ctypes.cast(self._ptrs, ctypes.c_void_p), self._hdl.world_size, self._hdl.rank,
-                                                  ctypes.c_uint64(self.grads.storage.numel()), ctypes.c_uint64(self._mc), st))
-            self._hdl.barrier(channel=1)
+                                                  ctypes.c_uint64(self.grads.padded), ctypes.c_uint64(self._mc), flags,
+                                                  ctypes.c_uint32(self._epoch), st))
+            if not self._inkernel:
+                self._hdl.barrier(channel=1)
         else:
             dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
         return self.grads.flat

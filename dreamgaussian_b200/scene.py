@@ -137,6 +137,12 @@ def to_raw_parameters(cloud: dict, seed: int = 0) -> dict:
 
 
 def bench_views(n: int, width: int, height: int, radius: float = 2.0):
-    """The fixed benchmark camera set of SURVEY.md §8(d): orbit(0, 0) then 45-degree azimuth steps."""
-    return [orbit_camera(0.0, (45.0 * i) % 360.0 - (360.0 if (45.0 * i) % 360.0 >= 180.0 else 0.0), radius, width, height)
-            for i in range(n)]
+    """The fixed benchmark camera set of SURVEY.md §8(d): orbit(0, 0) then 45-degree azimuth steps; beyond 8 views further
+    rings of 8 at other elevations (the reference samples elevation in [-30, 30], main.py:213-216), each ring turned a bit."""
+    elev = (0.0, 15.0, -15.0, 30.0, -30.0, 7.5, -7.5, 22.5)
+    cams = []
+    for i in range(n):
+        ring = i // 8
+        az = (45.0 * i + 5.625 * ring) % 360.0
+        cams.append(orbit_camera(elev[ring % 8], az - (360.0 if az >= 180.0 else 0.0), radius, width, height))
+    return cams

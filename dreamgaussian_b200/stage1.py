@@ -10,8 +10,9 @@ main.py:182-287 (train_step).  What changes:
   * rendering goes through FusedGaussianRasterizer (row f1): activations, SH dc/rest split and the three densification
     statistics happen inside the per-Gaussian kernels;
   * initial scales come from this library's distCUDA2 (row f3).
-The densification itself (a handful of boolean masks every 100 steps) is host logic on device tensors, device-agnostic on
-purpose: tests/test_stage1_cpu.py runs it on the CPU against outputs of the reference's own methods."""
+The densification exists twice: as device-agnostic tensor logic (tests/test_stage1_cpu.py runs it on the CPU against outputs
+of the reference's own methods) and as stream-compaction kernels (dgr_densify_plan / dgr_densify_apply, csrc/dgr_densify.cuh)
+that the CUDA loop uses and tests/test_stage1_gpu.py pins against the same reference outputs."""
 import ctypes
 import math
 from typing import NamedTuple, Optional
@@ -220,7 +221,47 @@ class GaussianModelB200:
             m = m | (self.stats.max_radii2D > max_screen_size) | (torch.exp(self.p["scaling"].detach()).max(dim=1).values > 0.1 * extent)
         return m
 
+    def _densify_fused(self, max_grad, min_opacity, extent, max_screen_size, noise=None):
+        """densify_and_prune as two launches of compaction kernels (csrc/dgr_densify.cuh: classify + block scan, then ONE pass
+        that writes the six parameter tensors and both Adam moments in the reference's final order) with one host read-back
+        of the new point count between them — instead of ~30 boolean-mask indexing / torch.cat calls."""
+        lib = _lib.load()
+        P, dev = self.num_points, self.p["xyz"].device
+        with torch.no_grad(), torch.cuda.device(dev):
+            st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            scratch = torch.empty((lib.dgr_densify_scratch_bytes(P),), dtype=torch.uint8, device=dev)
+            if getattr(self, "_counts_host", None) is None:
+                self._counts_host = torch.zeros((4,), dtype=torch.int32).pin_memory()
+            acc, den = self.stats.xyz_gradient_accum.contiguous(), self.stats.denom.contiguous()
+            _lib.check(lib.dgr_densify_plan(P, acc.data_ptr(), den.data_ptr(), self.p["opacity"].data_ptr(), self.p["scaling"].data_ptr(),
+                                            float(max_grad), float(self.percent_dense * extent), float(min_opacity), float(0.1 * extent),
+                                            1 if max_screen_size else 0, scratch.data_ptr(), self._counts_host.data_ptr(), st))
+            torch.cuda.current_stream(dev).synchronize()
+            n_keep, n_clone, n_sel, n_child = (int(x) for x in self._counts_host)
+            n_out = n_keep + n_clone + 2 * n_child
+            if noise is None:
+                noise = torch.randn((max(2 * n_sel, 1), 3), device=dev)
+            else:                                   # tests hand over the reference's draws: row = child * n_selected + rank
+                noise = noise.to(torch.empty((2 * n_sel, 3), device=dev)) if hasattr(noise, "to") else noise
+            noise = noise.contiguous().float()
+            t = _lib.DgrDensifyTensors()
+            new_p, new_m, new_v, keep = {}, {}, {}, [noise, scratch]
+            for i, k in enumerate(GROUPS):
+                src = self.p[k].detach()
+                w = int(src[0].numel()) if src.shape[0] else int(np.prod(src.shape[1:]))
+                new_p[k] = torch.empty((n_out,) + tuple(src.shape[1:]), dtype=torch.float32, device=dev)
+                new_m[k], new_v[k] = torch.empty_like(new_p[k]), torch.empty_like(new_p[k])
+                t.inp[i], t.exp_avg_in[i], t.exp_avg_sq_in[i] = src.data_ptr(), self.exp_avg[k].data_ptr(), self.exp_avg_sq[k].data_ptr()
+                t.out[i], t.exp_avg_out[i], t.exp_avg_sq_out[i] = new_p[k].data_ptr(), new_m[k].data_ptr(), new_v[k].data_ptr()
+                t.width[i] = w
+            _lib.check(lib.dgr_densify_apply(P, ctypes.byref(t), noise.data_ptr(), scratch.data_ptr(), st))
+            self.p = {k: v.requires_grad_(True) for k, v in new_p.items()}
+            self.exp_avg, self.exp_avg_sq = new_m, new_v
+        self._reset_stats()
+
     def densify_and_prune(self, max_grad, min_opacity, extent, max_screen_size, noise=None):
+        if getattr(self, "fused_densify", False) and self.p["xyz"].is_cuda and self.num_points > 0:
+            return self._densify_fused(max_grad, min_opacity, extent, max_screen_size, noise=noise)
         with torch.no_grad():
             grads = self.stats.xyz_gradient_accum / self.stats.denom
             grads[grads.isnan()] = 0.0
@@ -302,6 +343,7 @@ class Stage1Trainer:
         colors = self.rng.random((cfg.num_pts, 3)) / 255.0 * SH_C0 + 0.5                                         # SH2RGB(rand/255), gs_renderer.py:703-706
         self.gaussians = GaussianModelB200(cfg.sh_degree)
         self.gaussians.fused_adam = fused
+        self.gaussians.fused_densify = fused
         self.gaussians.create_from_points(cloud["means3D"], colors, spatial_lr_scale=10.0, device=device)      # gs_renderer.py:709
         self.gaussians.training_setup(optim)
         rgb, mask = synthetic_rgba(cfg.ref_size)

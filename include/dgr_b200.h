@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DGR_ABI_VERSION 2
+#define DGR_ABI_VERSION 3
 
 /* == GaussianRasterizationSettings, the 12-field NamedTuple built at gs_renderer.py:745-758 == */
 typedef struct DgrSettings {
@@ -144,9 +144,13 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom, const 
  * NVLink with this library's own kernel.  The buffer lives in symmetric memory: peer_ptrs[w] (HOST array of `world` device
  * addresses) is rank w's copy mapped into this process; multicast_ptr, if non-zero, is the NVSwitch multicast address of
  * the same buffer (then multimem.ld_reduce / multimem.st are used and peer_ptrs may be NULL).  n_floats % 4 == 0.
- * The caller synchronises the ranks (device-side barrier) before and after the call. */
+ * peer_flag_ptrs (HOST array of `world` device addresses, or NULL): rank w's flag area of dgr_peer_flag_bytes() bytes in
+ * the same symmetric allocation, zero-initialised once; with it the kernel carries its own two cross-rank barriers and
+ * `epoch` must be 1, 2, 3, ... over successive calls (the same value on every rank).  With NULL the caller synchronises the
+ * ranks (device-side barrier) before and after the call. */
+size_t dgr_peer_flag_bytes(void);
 int dgr_peer_allreduce(const uint64_t *peer_ptrs, int32_t world, int32_t rank, uint64_t n_floats, uint64_t multicast_ptr,
-                       void *stream);
+                       const uint64_t *peer_flag_ptrs, uint32_t epoch, void *stream);
 
 /* SURVEY.md §8 row f3 — replaces simple_knn._C.distCUDA2 (/root/reference/simple-knn/spatial.cu:15-26 -> SimpleKNN::knn,
  * simple_knn.cu:185-221; caller gs_renderer.py:341): mean_dists[i] = mean of the squared distances from point i to its 3
@@ -180,6 +184,31 @@ typedef struct DgrAdamGroup {
                        * whose .grad was None in some iteration lags behind) */
 } DgrAdamGroup;
 int dgr_adam_step(const DgrAdamGroup *groups, int32_t n_groups, double beta1, double beta2, double eps, void *stream);
+
+/* SURVEY.md §8 row f2 — the reference's densify_and_prune (/root/reference/gs_renderer.py:586-609 = densify_and_clone
+ * :582-600 + densify_and_split :555-580 + prune_points :509-513, with the optimizer-state surgery of :464-552) as stream
+ * compaction.  Two calls with ONE host read-back between them (the new point count sizes the output tensors):
+ *   dgr_densify_plan   classifies every point (grad = xyz_gradient_accum / denom, NaN -> 0; clone if |grad| >= grad_threshold
+ *                      and max(exp(scaling)) <= dense_extent; split if grad >= grad_threshold and max > dense_extent; pruned
+ *                      if sigmoid(opacity) < min_opacity or — when use_world != 0, the reference's `if max_screen_size:` —
+ *                      max(exp(scaling)) > max_world; max_radii2D never matters: densification_postfix has zeroed it, :551)
+ *                      and copies counts_host[4] = { kept originals, surviving clones, points selected for the split,
+ *                      surviving children per copy } (pinned host memory) — new point count = [0] + [1] + 2 * [3].
+ *   dgr_densify_apply  writes the new tensors in the reference's order (kept originals, clones, first children, second
+ *                      children): the six parameter tensors and both Adam moments (zero for new points).  A child's position is
+ *                      xyz + R(q/|q|) (noise[child * counts[2] + rank] * exp(scaling)), its scaling log(exp(scaling) / 1.6);
+ *                      noise = standard normals [2 * counts[2], 3] (device), rank = the point's rank among the selected.
+ * Tensor order in DgrDensifyTensors: xyz, f_dc, f_rest, opacity, scaling, rotation; width = floats per point (f_rest may be 0). */
+typedef struct DgrDensifyTensors {
+    const float *in[6], *exp_avg_in[6], *exp_avg_sq_in[6];
+    float *out[6], *exp_avg_out[6], *exp_avg_sq_out[6];
+    int32_t width[6];
+} DgrDensifyTensors;
+size_t dgr_densify_scratch_bytes(int32_t P);
+int dgr_densify_plan(int32_t P, const float *xyz_gradient_accum, const float *denom, const float *opacity_raw, const float *scaling_raw,
+                     float grad_threshold, float dense_extent, float min_opacity, float max_world, int32_t use_world,
+                     void *scratch, uint32_t *counts_host, void *stream);
+int dgr_densify_apply(int32_t P, const DgrDensifyTensors *t, const float *noise, const void *scratch, void *stream);
 
 /* GaussianRasterizer.markVisible: present[i] = 1 if Gaussian i passes the near-plane test. */
 int dgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,

@@ -69,6 +69,12 @@ class OracleResult:
         getattr(lib(), "dgr_oracle_get_flags_" + self._suf)(ctypes.c_void_p(self._ctx), _ptr(px), _ptr(g), ctypes.byref(n))
         return px, g[: self.P], int(n.value)
 
+    def tie_slack(self):
+        """[H,W] float32: how far resolving the pixel's float32 depth-key ties the other way can move its colour."""
+        out = np.zeros((self.H, self.W), np.float32)
+        getattr(lib(), "dgr_oracle_get_tie_slack_" + self._suf)(ctypes.c_void_p(self._ctx), _ptr(out))
+        return out
+
     def state(self):
         P = max(self.P, 1)
         px, py, dep = (np.zeros(P, self._dt) for _ in range(3))

@@ -15,6 +15,12 @@
  * PARITY UNPINNED: the reference ships no tests or golden vectors for this path.
  */
 
+#ifndef FLAG_G
+/* per-Gaussian ambiguity bits are OR-ed from several OpenMP threads */
+#define FLAG_G(g, bit) __atomic_fetch_or(&c->ambig_g[(g)], (unsigned char)(bit), __ATOMIC_RELAXED)
+/* a1 * a2 * T above which a depth tie between two consecutive contributors is treated as able to move other gradients */
+#define DGR_ORACLE_TIE_MATERIAL 1e-4
+#endif
 #define CAT_(a, b) a##_##b
 #define CAT(a, b) CAT_(a, b)
 #define FN(name) CAT(name, SUF)
@@ -34,7 +40,7 @@ typedef struct {
     /* binning */
     size_t N; unsigned *point_list; unsigned *ranges /*2 per tile*/;
     /* per-pixel */
-    unsigned *n_contrib; REAL *final_T; unsigned char *ambig_px;
+    unsigned *n_contrib; REAL *final_T; unsigned char *ambig_px; float *tie_slack;
     double eps;
 } FN(Ctx);
 
@@ -118,7 +124,7 @@ void FN(dgr_oracle_free)(FN(Ctx) *c) {
     free(c->means); free(c->shs); free(c->colors); free(c->opac); free(c->scales); free(c->rots); free(c->cov3d_in);
     free(c->px); free(c->py); free(c->depth); free(c->conic); free(c->cov2d); free(c->rgb); free(c->cov3d);
     free(c->radii); free(c->clamped); free(c->rect); free(c->ambig_g);
-    free(c->point_list); free(c->ranges); free(c->n_contrib); free(c->final_T); free(c->ambig_px);
+    free(c->point_list); free(c->ranges); free(c->n_contrib); free(c->final_T); free(c->ambig_px); free(c->tie_slack);
     free(c);
 }
 
@@ -283,19 +289,23 @@ FN(Ctx) *FN(dgr_oracle_forward)(
     size_t HW = (size_t)H * W;
     c->n_contrib = calloc(HW ? HW : 1, sizeof(unsigned)); c->final_T = calloc(HW ? HW : 1, sizeof(REAL));
     c->ambig_px = calloc(HW ? HW : 1, 1);
+    c->tie_slack = calloc(HW ? HW : 1, sizeof(float));
 #pragma omp parallel for schedule(dynamic, 1)
     for (int tile = 0; tile < gx * gy; tile++) {
         int tx0 = (tile % gx) * DGR_TILE, ty0 = (tile / gx) * DGR_TILE;
         unsigned s = c->ranges[2 * tile], e = c->ranges[2 * tile + 1];
         for (int yy = ty0; yy < ty0 + DGR_TILE && yy < H; yy++) for (int xx = tx0; xx < tx0 + DGR_TILE && xx < W; xx++) {
             REAL T = 1, C[3] = { 0, 0, 0 }, Dp = 0, Wt = 0; unsigned n = 0, last = 0;
-            REAL last_depth = -1; unsigned last_g = 0; int have_last = 0; unsigned char amb = 0;
+            REAL last_depth = -1, last_a = 0, last_T = 1; unsigned last_g = 0; int have_last = 0; unsigned char amb = 0;
+            double slack = 0;           /* how far resolving this pixel's depth ties the other way can move its colour */
+            unsigned tie_upto = 0;      /* list position (1-based) of the first member of the deepest MATERIAL depth tie */
+            unsigned last_n = 0;
             for (unsigned i = s; i < e; i++) {
                 unsigned g = c->point_list[i]; n++;
                 REAL dx = c->px[g] - (REAL)xx, dy = c->py[g] - (REAL)yy;
                 const REAL *co = c->conic + 3 * (size_t)g;
                 REAL power = (REAL)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
-                if (power > (REAL)-1e-7 && power < (REAL)1e-7) { amb |= 8; c->ambig_g[g] |= 1; }
+                if (power > (REAL)-1e-7 && power < (REAL)1e-7) { amb |= 8; FLAG_G(g, 1); }
                 if (power > 0) continue;
                 REAL og = c->opac[g] * (REAL)exp((double)power);
                 REAL a = FN(rmin)((REAL)DGR_ALPHA_MAX, og);
@@ -303,22 +313,45 @@ FN(Ctx) *FN(dgr_oracle_forward)(
                    error of `power` (= relative error of alpha) scales with the magnitude of those terms */
                 double mag = 0.5 * (fabs((double)co[0]) * (double)dx * (double)dx + fabs((double)co[2]) * (double)dy * (double)dy)
                            + fabs((double)co[1] * (double)dx * (double)dy);
-                if (fabs((double)a - (double)DGR_ALPHA_MIN) < eps * (1.0 + mag) * (double)DGR_ALPHA_MIN) { amb |= 1; c->ambig_g[g] |= 1; }
+                if (fabs((double)a - (double)DGR_ALPHA_MIN) < eps * (1.0 + mag) * (double)DGR_ALPHA_MIN) { amb |= 1; FLAG_G(g, 1); }
                 if (a < (REAL)DGR_ALPHA_MIN) continue;
                 REAL test_T = T * ((REAL)1 - a);
-                if (fabs((double)test_T - (double)DGR_T_STOP) < eps * (double)DGR_T_STOP && (double)(a * T) > 1e-5) { amb |= 2; c->ambig_g[g] |= 1; }
+                if (fabs((double)test_T - (double)DGR_T_STOP) < eps * (double)DGR_T_STOP && (double)(a * T) > 1e-5) { amb |= 2; FLAG_G(g, 1); }
                 if (test_T < (REAL)DGR_T_STOP) break;
                 if (have_last && fabs((double)c->depth[g] - (double)last_depth) < 1e-6 * (double)c->depth[g]) {   /* ~8 float32 ulps */
-                    amb |= 4; c->ambig_g[g] |= 2; c->ambig_g[last_g] |= 2; }
-                have_last = 1; last_depth = c->depth[g]; last_g = g;
+                    amb |= 4; FLAG_G(g, 2); FLAG_G(last_g, 2);
+                    /* Swapping the two leaves everything behind them untouched (the product of their (1 - alpha) is the same)
+                       but changes the "sum behind" that every Gaussian IN FRONT of them sees by ~ a1 a2 T (s1 - s2): material
+                       when both are reasonably opaque and little has been absorbed yet. */
+                    double dc = 0;
+                    for (int ch = 0; ch < 3; ch++) { double d = fabs((double)c->rgb[3 * (size_t)g + ch] - (double)c->rgb[3 * (size_t)last_g + ch]); if (d > dc) dc = d; }
+                    slack += (double)last_a * (double)a * (double)last_T * dc;
+                    if ((double)last_a * (double)a * (double)last_T > DGR_ORACLE_TIE_MATERIAL) tie_upto = last_n;
+                }
+                have_last = 1; last_depth = c->depth[g]; last_g = g; last_a = a; last_T = T; last_n = n;
                 REAL w = a * T;
                 for (int ch = 0; ch < 3; ch++) C[ch] += c->rgb[3 * (size_t)g + ch] * w;
                 Dp += c->depth[g] * w; Wt += w; T = test_T; last = n;
             }
+            if (tie_upto > 1) {
+                /* propagate: every Gaussian compositing in front of a material tied pair at this pixel may legitimately see a
+                   different gradient from a float32 implementation that resolves the tie the other way (bit 16) */
+                unsigned m = 0;
+                for (unsigned i = s; i < e && m + 1 < tie_upto; i++) {
+                    unsigned g = c->point_list[i]; m++;
+                    REAL dx = c->px[g] - (REAL)xx, dy = c->py[g] - (REAL)yy;
+                    const REAL *co = c->conic + 3 * (size_t)g;
+                    REAL power = (REAL)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                    if (power > 0) continue;
+                    REAL a = FN(rmin)((REAL)DGR_ALPHA_MAX, c->opac[g] * (REAL)exp((double)power));
+                    if (a < (REAL)DGR_ALPHA_MIN) continue;
+                    FLAG_G(g, 16);
+                }
+            }
             size_t pix = (size_t)yy * W + xx;
             for (int ch = 0; ch < 3; ch++) out_color[ch * HW + pix] = C[ch] + T * c->bg[ch];
             out_depth[pix] = Dp; out_alpha[pix] = Wt;
-            c->n_contrib[pix] = last; c->final_T[pix] = T; c->ambig_px[pix] = amb;
+            c->n_contrib[pix] = last; c->final_T[pix] = T; c->ambig_px[pix] = amb; c->tie_slack[pix] = (float)slack;
         }
     }
     return c;
@@ -329,6 +362,9 @@ void FN(dgr_oracle_get_flags)(const FN(Ctx) *c, unsigned char *ambig_px, unsigne
     if (ambig_g) memcpy(ambig_g, c->ambig_g, (size_t)c->P);
     if (N) *N = c->N;
 }
+
+/* per pixel: sum over its depth ties of a1 a2 T max|rgb1 - rgb2| = how far the other resolution of the ties moves the colour */
+void FN(dgr_oracle_get_tie_slack)(const FN(Ctx) *c, float *out) { memcpy(out, c->tie_slack, (size_t)c->H * c->W * sizeof(float)); }
 
 /* intermediate state, for kernel-by-kernel parity checks */
 void FN(dgr_oracle_get_state)(const FN(Ctx) *c, REAL *px, REAL *py, REAL *depth, REAL *conic, REAL *rgb, int *rect) {

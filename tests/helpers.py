@@ -57,7 +57,7 @@ def run_oracle(settings, inputs, grads=None, dtype=np.float64, eps=2e-5):
     r = c_oracle.forward(**settings, **inputs, dtype=dtype, eps=eps)
     out = dict(color=r.color, depth=r.depth, alpha=r.alpha, radii=r.radii)
     apx, ag, n = r.flags()
-    out.update(ambig_px=apx, ambig_g=ag, n_inst=n)
+    out.update(ambig_px=apx, ambig_g=ag, n_inst=n, tie_slack=r.tie_slack())
     if grads is not None:
         out["grads"] = r.backward(*grads)
     r.close()

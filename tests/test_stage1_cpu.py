@@ -25,6 +25,7 @@ def _model_from_golden(device="cpu"):
     m = stage1.GaussianModelB200(1)
     m.spatial_lr_scale = 10
     m.fused_adam = device != "cpu"
+    m.fused_densify = device != "cpu"
     m._set({k: torch.tensor(GOLD["init_" + k], device=device) for k in NAMES})
     m.training_setup(stage1.OptimConfig())
     return m

@@ -64,3 +64,77 @@ def test_stage1_loop_fused_tracks_the_reference_formulation_and_densifies():
     assert a.gaussians.stats.denom.shape[0] == a.gaussians.num_points
     assert all(t.shape[0] == a.gaussians.num_points for t in a.gaussians.exp_avg.values())
     assert losses[-1] < losses[0]                       # the known-view MSE terms pull the loss down
+
+
+def _golden_noise():
+    noise = torch.tensor(cpu.GOLD["split_noise"])
+
+    class Noise:                                   # sized lazily: the number of split points is known inside
+        def to(self, stds):
+            return noise[: stds.shape[0]].to(stds)
+    return Noise()
+
+
+def test_densify_compaction_kernels_reproduce_the_reference_methods():
+    """dgr_densify_plan / dgr_densify_apply against the output of the reference's own densify_and_prune
+    (tests/golden/make_golden_stage1.py: 400 -> 684 points, parameters and both Adam moments), then reset_opacity + one more
+    optimiser step against the reference's."""
+    m = cpu._model_from_golden("cuda")
+    assert m.fused_densify
+    cpu._two_adam_steps(m)
+    m.stats.xyz_gradient_accum = torch.tensor(cpu.GOLD["stats_xyz_gradient_accum"], device="cuda").reshape(-1)
+    m.stats.denom = torch.tensor(cpu.GOLD["stats_denom"], device="cuda").reshape(-1)
+    m.stats.max_radii2D = torch.tensor(cpu.GOLD["stats_max_radii2D"], device="cuda").reshape(-1)
+    m.densify_and_prune(0.01, min_opacity=0.01, extent=4, max_screen_size=1, noise=_golden_noise())
+    assert m.num_points == cpu.GOLD["after_densify_xyz"].shape[0] == 684
+    cpu.check_against(m, "after_densify_", rtol=3e-6, atol=1e-7)
+    assert not m.stats.xyz_gradient_accum.any() and m.stats.denom.shape[0] == 684
+    m.reset_opacity()
+    cpu.check_against(m, "after_reset_", rtol=3e-6, atol=1e-7)
+    m.update_learning_rate(3)
+    for k in stage1.GROUPS:
+        m.p[k].grad = torch.tensor(cpu.GOLD["grad3_" + k], device="cuda")
+    m.optimizer_step()
+    cpu.check_against(m, "after_reset_adam_", rtol=5e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("P,deg,screen", [(5000, 0, 1), (30011, 3, 0), (257, 1, 1), (1, 0, 1)])
+def test_densify_compaction_equals_the_tensor_indexing_path(P, deg, screen):
+    """Same decisions, same order, same values as the device-agnostic restatement (stage1.py, pinned on the CPU by the
+    reference's outputs) on random models, including the no-world-size-prune variant and tiny point counts."""
+    rng = np.random.default_rng(P)
+    M = (deg + 1) ** 2
+    init = dict(xyz=rng.normal(0, 0.3, (P, 3)), f_dc=rng.normal(0, 1, (P, 1, 3)), f_rest=rng.normal(0, 0.1, (P, M - 1, 3)),
+                opacity=rng.normal(-1.0, 2.5, (P, 1)), scaling=rng.normal(-3.4, 0.6, (P, 3)), rotation=rng.normal(0, 1, (P, 4)))
+    models = []
+    for fused in (True, False):
+        m = stage1.GaussianModelB200(deg)
+        m.fused_adam, m.fused_densify = True, fused
+        m._set({k: torch.tensor(v, dtype=torch.float32, device="cuda") for k, v in init.items()})
+        m.training_setup()
+        for k in stage1.GROUPS:
+            m.exp_avg[k] = torch.tensor(rng.normal(0, 1, init[k].shape), dtype=torch.float32, device="cuda")
+            m.exp_avg_sq[k] = m.exp_avg[k] ** 2
+        models.append(m)
+    for k in stage1.GROUPS:
+        models[1].exp_avg[k] = models[0].exp_avg[k].clone(); models[1].exp_avg_sq[k] = models[0].exp_avg_sq[k].clone()
+    acc = torch.tensor(np.abs(rng.normal(0, 0.02, (P,))).astype(np.float32) * 3, device="cuda")
+    den = torch.tensor(rng.integers(0, 4, (P,)).astype(np.float32), device="cuda")
+    draws = torch.randn((2 * P, 3), device="cuda")
+
+    class Noise:                                   # both paths read row child * n_selected + rank of the same draws
+        def to(self, stds):
+            return draws[: stds.shape[0]].to(stds)
+    noise = Noise()
+    for m in models:
+        m.stats.xyz_gradient_accum, m.stats.denom = acc.clone(), den.clone()
+        m.densify_and_prune(0.01, min_opacity=0.01, extent=4, max_screen_size=screen, noise=noise)
+    a, b = models
+    assert a.num_points == b.num_points
+    for k in stage1.GROUPS:
+        if a.p[k].numel() == 0:
+            assert a.p[k].shape == b.p[k].shape
+            continue
+        scale = max(1.0, float(b.p[k].abs().max()))
+        assert float((a.p[k] - b.p[k]).abs().max()) <= 3e-6 * scale, k
+        assert torch.equal(a.exp_avg[k], b.exp_avg[k]) and torch.equal(a.exp_avg_sq[k], b.exp_avg_sq[k]), k

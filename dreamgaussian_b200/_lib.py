@@ -111,7 +111,7 @@ def load():
     lib.dgr_event_destroy.argtypes = [vp]
     lib.dgr_forward_render.restype = ctypes.c_int
     lib.dgr_forward_render.argtypes = [ctypes.POINTER(DgrSettings), ctypes.POINTER(DgrGaussians), vp, vp, u64, vp,
-                                       ctypes.POINTER(DgrImages), i32, vp, vp, vp]
+                                       ctypes.POINTER(DgrImages), i32, vp, u64, vp, vp]
     lib.dgr_backward.restype = ctypes.c_int
     lib.dgr_backward.argtypes = [ctypes.POINTER(DgrSettings), ctypes.POINTER(DgrGaussians), vp, vp, u64, vp, vp, vp,
                                  ctypes.POINTER(DgrImageGrads), ctypes.POINTER(DgrGaussianGrads), vp]

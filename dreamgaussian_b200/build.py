@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libdgr_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
-    "--expt-relaxed-constexpr", "-Xptxas", "-v",
+    "--expt-relaxed-constexpr", "-Xptxas", "-v", "-ldl",
 ]
 
 

@@ -2,12 +2,15 @@
 // layout, kernel launches on the caller's stream.  No torch, no library kernels (no CUB/cuBLAS), no CPU fallback:
 // without a CUDA device every compute entry point fails with an error string.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/dgr_b200.h"
@@ -27,6 +30,12 @@ using namespace dgr;
 namespace {
 thread_local std::string g_err;
 thread_local uint64_t g_launches = 0;
+
+// NVTX range around every C-ABI entry point (tracing): header-only NVTX v3, a no-op unless a tool is attached
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 int fail(int code, const char *what, const char *detail = nullptr) {
     g_err = what;
@@ -68,6 +77,27 @@ inline void prof_end(cudaStream_t st) {
             if (e_ != cudaSuccess) return fail((int)e_, name, cudaGetErrorString(e_)); }       \
     } while (0)
 
+// Kernel launch with the programmatic-dependent-launch attribute: the kernel may become resident while its predecessor in
+// the stream (which must be a kernel, not a copy / memset / event) is still running; it calls pdl_wait() before it touches
+// anything the predecessor produces.  g_pdl = 0 (DGR_PDL=0 or dgr_set_tuning bit 3) launches the same kernels the ordinary way.
+std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+    int v = g_pdl.load();
+    if (v < 0) { const char *e = getenv("DGR_PDL"); v = (e && e[0] == '0') ? 0 : 1; g_pdl = v; }
+    return v != 0;
+}
+template <class... KArgs, class... Args>
+void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    const bool on = pdl && pdl_enabled();
+    cfg.attrs = on ? attr : nullptr; cfg.numAttrs = on ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);       // errors surface through cudaGetLastError in DGR_KERNEL
+}
+
 int check_settings(const DgrSettings *s) {
     if (!s) return fail(-1, "settings is NULL");
     if (s->image_height <= 0 || s->image_width <= 0) return fail(-1, "image size must be positive");
@@ -108,7 +138,7 @@ void launch_pre_fwd(const DgrSettings *s, const DgrGaussians *g, int *radii, cha
     const size_t smem = (size_t)L.tiles * 4;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV, RAW><<<L.nblocks, kPreThreads, smem, st>>>(
+    launch_k(preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV, RAW>, dim3(L.nblocks), dim3(kPreThreads), smem, st, false,
         g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
         s->campos, g->means3D, g->shs, g->shs_rest, g->colors_precomp, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii,
         reinterpret_cast<Rec *>(geom + L.off_rec), reinterpret_cast<unsigned *>(geom + L.off_touched),
@@ -119,7 +149,7 @@ template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
 void launch_pre_bwd(const DgrSettings *s, const DgrGaussians *g, const int *radii, const unsigned *touched, const float *grad_rec,
                     const DgrGaussianGrads *o, cudaStream_t st) {
     const int nb = (g->P + kPreThreads - 1) / kPreThreads;
-    preprocess_bwd_kernel<DEG, HAS_SH, HAS_COV, RAW><<<nb, kPreThreads, 0, st>>>(
+    launch_k(preprocess_bwd_kernel<DEG, HAS_SH, HAS_COV, RAW>, dim3(nb), dim3(kPreThreads), 0, st, true,
         g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
         s->campos, g->means3D, g->shs, g->shs_rest, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii, touched, grad_rec,
         o->dL_dmeans3D, o->dL_dmeans2D, o->dL_dshs, o->dL_dcolors_precomp, o->dL_dopacities, o->dL_dscales, o->dL_drotations,
@@ -247,6 +277,7 @@ int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order) {
     if ((ppl_fwd != 1 && ppl_fwd != 2 && ppl_fwd != 4) || (ppl_bwd != 1 && ppl_bwd != 2 && ppl_bwd != 4)) return fail(-1, "ppl must be 1, 2 or 4");
     g_ppl_fwd = ppl_fwd; g_ppl_bwd = ppl_bwd == 4 ? 2 : ppl_bwd;          // the backward has 8x4 and 8x8 sub-tiles
     g_no_order = (tile_order & 3) == 0;
+    g_pdl = (tile_order & 8) ? 0 : 1;                   // bit 3: programmatic dependent launches OFF (A/B switch)
     return 0;
 }
 
@@ -263,6 +294,7 @@ size_t dgr_image_bytes(int32_t H, int32_t W) { return ImageLayout(H, W).total; }
 size_t dgr_binning_bytes(uint64_t cap, int32_t H, int32_t W) { (void)H; (void)W; return BinningLayout(cap).total; }
 
 int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *geom_v, void *image_v, int32_t *radii, void *stream) {
+    NvtxRange nvtx_("dgr_forward_preprocess");
     if (int e = check_settings(s)) return e;
     if (int e = check_gaussians(s, g)) return e;
     cudaStream_t st = (cudaStream_t)stream;
@@ -281,8 +313,9 @@ int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *ge
 }
 
 int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v, void *binning_v, uint64_t capacity,
-                       void *image_v, const DgrImages *out, int32_t flags, uint64_t *counts_host, void *count_ready_event,
-                       void *stream) {
+                       void *image_v, const DgrImages *out, int32_t flags, uint64_t *counts_host, uint64_t ticket,
+                       void *count_ready_event, void *stream) {
+    NvtxRange nvtx_("dgr_forward_render");
     if (int e = check_settings(s)) return e;
     if (!g || !geom_v || !image_v || !out) return fail(-1, "NULL argument");
     if (!out->color || !out->depth || !out->alpha) return fail(-1, "output images must not be NULL");
@@ -314,28 +347,34 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
     if (!dv) return -1;
     (void)(flags & DGR_FLAG_RERUN);           // a re-run only repeats the scan from the (still valid) per-tile totals
     DGR_KERNEL("tile_scan", st, s->debug,
-               tile_scan_kernel<<<1, 1024, 0, st>>>(tiles, tile_count, (unsigned long long)capacity, ranges, tile_cursor, hdr, tile_order, work, big_list));
-    if (counts_host)      // { n_instances, n_big_tiles }
-        DGR_CUDA(cudaMemcpyAsync(counts_host, geom, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    if (count_ready_event) DGR_CUDA(cudaEventRecord((cudaEvent_t)count_ready_event, st));
+               launch_k(tile_scan_kernel, dim3(1), dim3(1024), 0, st, true, tiles, (const unsigned *)tile_count, (unsigned long long)capacity, ranges,
+                        tile_cursor, hdr, tile_order, work, big_list, (volatile unsigned long long *)(ticket ? counts_host : nullptr),
+                        (unsigned long long)ticket));
+    if (!ticket) {            // copy + event between the kernels (this also ends the chain of programmatic dependent launches here)
+        if (counts_host)      // { n_instances, n_big_tiles }
+            DGR_CUDA(cudaMemcpyAsync(counts_host, geom, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        if (count_ready_event) DGR_CUDA(cudaEventRecord((cudaEvent_t)count_ready_event, st));
+    }
     if (g->P > 0 && capacity > 0) {
         const size_t smem = (size_t)tiles * 4;
         DGR_KERNEL("emit_instances", st, s->debug,
-                   emit_instances_kernel<<<GL.nblocks, kPreThreads, smem, st>>>(
-                       g->P, IL.gx, tiles, GL.iters, rec, reinterpret_cast<const unsigned *>(geom + GL.off_touched), ranges, tile_cursor, keys));
+                   launch_k(emit_instances_kernel, dim3(GL.nblocks), dim3(kPreThreads), smem, st, true, g->P, IL.gx, tiles, GL.iters, rec,
+                            reinterpret_cast<const unsigned *>(geom + GL.off_touched), (const uint2 *)ranges, tile_cursor, keys));
         DGR_KERNEL("tile_sort_gather", st, s->debug,
-                   tile_sort_gather_kernel<<<tiles, kSortSmallThreads, SmS::bytes, st>>>(tile_order, ranges, keys, rec, ids, recs));
+                   launch_k(tile_sort_gather_kernel, dim3(tiles), dim3(kSortSmallThreads), SmS::bytes, st, true, (const unsigned *)tile_order,
+                            (const uint2 *)ranges, keys, rec, ids, recs));
         if (flags & DGR_FLAG_BIG_TILES)
             DGR_KERNEL("tile_sort_gather_big", st, s->debug,
-                       tile_sort_gather_big_kernel<<<dv->big_grid, kSortBigThreads, SmB::bytes, st>>>(work, big_list, ranges, keys, rec, ids, recs));
+                       launch_k(tile_sort_gather_big_kernel, dim3(dv->big_grid), dim3(kSortBigThreads), SmB::bytes, st, true, (const TileWork *)work,
+                                (const unsigned *)big_list, (const uint2 *)ranges, keys, rec, ids, recs));
     }
     // persistent forward render: every (tile, sub-tile) is a work item, handed out heaviest tile first
     const int ppl = g_ppl_fwd.load();
 #define DGR_RENDER_FWD(PPL_, GRID_)                                                                             \
     DGR_KERNEL("render_fwd", st, s->debug,                                                                      \
-               render_fwd_kernel<PPL_><<<(unsigned)min(GRID_, (tiles * SubTile<PPL_>::kPerTile + kRenderWarps - 1) / kRenderWarps), kRenderThreads, 0, st>>>(   \
-                   H, W, IL.gx, tile_order, (unsigned)(tiles * SubTile<PPL_>::kPerTile), &work->fwd_next, ranges, recs, s->bg,         \
-                   out->color, out->depth, out->alpha, n_contrib, final_T))
+               launch_k(render_fwd_kernel<PPL_>, dim3((unsigned)min(GRID_, (tiles * SubTile<PPL_>::kPerTile + kRenderWarps - 1) / kRenderWarps)),   \
+                        dim3(kRenderThreads), 0, st, true, H, W, IL.gx, (const unsigned *)tile_order, (unsigned)(tiles * SubTile<PPL_>::kPerTile),       \
+                        &work->fwd_next, (const uint2 *)ranges, (const Rec *)recs, s->bg, out->color, out->depth, out->alpha, n_contrib, final_T))
     if (ppl == 4) DGR_RENDER_FWD(4, dv->fwd_grid[2]); else if (ppl == 2) DGR_RENDER_FWD(2, dv->fwd_grid[1]); else DGR_RENDER_FWD(1, dv->fwd_grid[0]);
 #undef DGR_RENDER_FWD
     return 0;
@@ -344,6 +383,7 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
 int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, const void *binning_v, uint64_t capacity,
                  const void *image_v, const int32_t *radii, const float *out_alpha, const DgrImageGrads *gin,
                  const DgrGaussianGrads *gout, void *stream) {
+    NvtxRange nvtx_("dgr_backward");
     (void)out_alpha;
     if (int e = check_settings(s)) return e;
     if (int e = check_gaussians(s, g)) return e;
@@ -387,6 +427,7 @@ size_t dgr_peer_flag_bytes(void) { return (size_t)2 * kMaxFlagBlocks * kMaxPeers
 
 int dgr_peer_allreduce(const uint64_t *peer_ptrs, int32_t world, int32_t rank, uint64_t n_floats, uint64_t multicast_ptr,
                        const uint64_t *peer_flag_ptrs, uint32_t epoch, void *stream) {
+    NvtxRange nvtx_("dgr_peer_allreduce");
     if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(-1, "bad world / rank");
     if (n_floats % 4 != 0) return fail(-1, "n_floats must be a multiple of 4");
     if (!peer_ptrs && !multicast_ptr) return fail(-1, "no peer pointers");
@@ -419,6 +460,7 @@ int dgr_peer_allreduce(const uint64_t *peer_ptrs, int32_t world, int32_t rank, u
 size_t dgr_knn_scratch_bytes(int32_t P) { return KnnLayout(P).total; }
 
 int dgr_dist_cuda2(int32_t P, const float *points, float *mean_dists, void *scratch_v, void *stream) {
+    NvtxRange nvtx_("dgr_dist_cuda2");
     if (P < 0) return fail(-1, "P < 0");
     if (P == 0) return 0;
     if (!points || !mean_dists || !scratch_v) return fail(-1, "NULL argument");
@@ -454,6 +496,7 @@ size_t dgr_fields_scratch_bytes(int32_t P, int32_t num_blocks) { return FieldsLa
 int dgr_extract_fields(int32_t P, const float *xyz, const float *opacity_raw, const float *scaling_raw, const float *rotation_raw,
                        int32_t resolution, int32_t num_blocks, float relax_ratio, float *occ, float *center_scale, void *scratch_v,
                        void *stream) {
+    NvtxRange nvtx_("dgr_extract_fields");
     if (P < 0 || resolution < 2 || num_blocks < 1) return fail(-1, "bad P / resolution / num_blocks");
     if (resolution % num_blocks != 0) return fail(-2, "resolution must be a multiple of num_blocks");
     if (num_blocks > 64) return fail(-3, "num_blocks above 64 not supported");
@@ -494,6 +537,7 @@ int dgr_extract_fields(int32_t P, const float *xyz, const float *opacity_raw, co
 }
 
 int dgr_adam_step(const DgrAdamGroup *groups, int32_t n_groups, double beta1, double beta2, double eps, void *stream) {
+    NvtxRange nvtx_("dgr_adam_step");
     if (!groups || n_groups < 1 || n_groups > kAdamMaxGroups) return fail(-1, "dgr_adam_step: 1..8 groups");
     AdamGroups G;
     G.n_groups = n_groups;
@@ -524,6 +568,7 @@ size_t dgr_densify_scratch_bytes(int32_t P) { return DensifyLayout(P).total; }
 int dgr_densify_plan(int32_t P, const float *xyz_gradient_accum, const float *denom, const float *opacity_raw, const float *scaling_raw,
                      float grad_threshold, float dense_extent, float min_opacity, float max_world, int32_t use_world,
                      void *scratch_v, uint32_t *counts_host, void *stream) {
+    NvtxRange nvtx_("dgr_densify_plan");
     if (P < 0) return fail(-1, "P < 0");
     if (!scratch_v || (P > 0 && (!xyz_gradient_accum || !denom || !opacity_raw || !scaling_raw))) return fail(-1, "NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
@@ -544,6 +589,7 @@ int dgr_densify_plan(int32_t P, const float *xyz_gradient_accum, const float *de
 }
 
 int dgr_densify_apply(int32_t P, const DgrDensifyTensors *t, const float *noise, const void *scratch_v, void *stream) {
+    NvtxRange nvtx_("dgr_densify_apply");
     if (P < 0 || !t || !scratch_v) return fail(-1, "bad argument");
     if (P == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -567,6 +613,7 @@ int dgr_densify_apply(int32_t P, const DgrDensifyTensors *t, const float *noise,
 
 int dgr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
                      uint8_t *present, void *stream) {
+    NvtxRange nvtx_("dgr_mark_visible");
     (void)projmatrix;
     if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(-1, "bad argument");
     if (P == 0) return 0;

@@ -112,10 +112,6 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
         if (HAS_COV && dL_dcov3D) { for (int k = 0; k < 6; k++) dL_dcov3D[6 * (size_t)g + k] = 0.f; }
     }
     if (visible) {
-        const float4 m0 = ldg_f4(grad_rec + (size_t)g * kGradRecFloats);
-        const float4 m1 = ldg_f4(grad_rec + (size_t)g * kGradRecFloats + 4);
-        const float4 m2 = ldg_f4(grad_rec + (size_t)g * kGradRecFloats + 8);
-        // moments: m0 = {u, u dx, u dy, u dx^2}, m1 = {u dx dy, u dy^2, wr, wg}, m2 = {wb, wd, -, -}
         const float3 p = make_float3(__ldg(means3D + 3 * (size_t)g), __ldg(means3D + 3 * (size_t)g + 1), __ldg(means3D + 3 * (size_t)g + 2));
         float S6[6];
         float R[9];
@@ -141,6 +137,14 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
         const float det = a * c - b * b, di = 1.f / det;
         const float cA = c * di, cB = -b * di, cC = a * di;
         const float o = RAW ? act_sigmoid(__ldg(opacities + g)) : __ldg(opacities + g);
+
+        // Everything above reads only the op's inputs: under a programmatic dependent launch it overlaps the tail of the
+        // backward render kernel.  The moments that kernel accumulates are complete after this point.
+        pdl_wait();
+        const float4 m0 = ldg_f4(grad_rec + (size_t)g * kGradRecFloats);
+        const float4 m1 = ldg_f4(grad_rec + (size_t)g * kGradRecFloats + 4);
+        const float4 m2 = ldg_f4(grad_rec + (size_t)g * kGradRecFloats + 8);
+        // moments: m0 = {u, u dx, u dy, u dx^2}, m1 = {u dx dy, u dy^2, wr, wg}, m2 = {wb, wd, -, -}
 
         // pixel-space mean gradient and conic gradient from the moments
         const float gpx = -(cA * m0.y + cB * m0.z), gpy = -(cC * m0.z + cB * m0.y);

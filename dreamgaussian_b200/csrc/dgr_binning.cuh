@@ -165,8 +165,19 @@ tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int tiles, const unsigned *__restrict__ tile_count, unsigned long long cap, uint2 *__restrict__ ranges,
                  unsigned *__restrict__ tile_cursor, GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order,
-                 TileWork *__restrict__ work, unsigned *__restrict__ big_list) {
+                 TileWork *__restrict__ work, unsigned *__restrict__ big_list,
+                 volatile unsigned long long *counts_host, unsigned long long ticket) {
+    pdl_trigger();
+    pdl_wait();                          // the per-tile totals of the preprocess kernel are complete
     tile_scan_cta(tiles, tile_count, cap, ranges, tile_cursor, hdr, tile_order, work, big_list);
+    // The host wants the instance count early (is the caller's capacity guess large enough?).  With a ticket the counts go
+    // straight into the caller's pinned, device-mapped host memory — no copy or event between this kernel and the next, so
+    // the rest of the forward chains behind it with programmatic dependent launches while the host polls the ticket.
+    if (counts_host && ticket && threadIdx.x == 0) {
+        counts_host[0] = hdr->n_inst; counts_host[1] = hdr->n_big;
+        __threadfence_system();
+        counts_host[2] = ticket;
+    }
 }
 
 // Same block <-> Gaussian mapping as the preprocess kernel.  Pass 1 counts the block's instances per tile in shared
@@ -178,7 +189,9 @@ emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, const Rec *__rest
                       const uint2 *__restrict__ ranges, unsigned *__restrict__ tile_cursor,
                       unsigned long long *__restrict__ keys) {
     extern __shared__ unsigned s_off[];
+    pdl_trigger();
     for (int t = threadIdx.x; t < tiles; t += kPreThreads) s_off[t] = 0u;
+    pdl_wait();                          // ranges / cursors of the tile scan (and, transitively, the preprocess outputs)
     __syncthreads();
     // pass 1: per-tile counts of this block (the same AABB walk as the preprocess histogram)
     for (int it = 0; it < gpb_iters; it++) {
@@ -355,6 +368,8 @@ __global__ void __launch_bounds__(kSortSmallThreads)
 tile_sort_gather_kernel(const unsigned *__restrict__ tile_order, const uint2 *__restrict__ ranges, unsigned long long *__restrict__ keys,
                         const Rec *__restrict__ rec, unsigned *__restrict__ ids_sorted, Rec *__restrict__ rec_sorted) {
     extern __shared__ __align__(16) unsigned char s_sort[];
+    pdl_trigger();
+    pdl_wait();
     const uint2 r = ranges[tile_order[blockIdx.x]];
     const int n = (int)(r.y - r.x);
     if (n <= 0 || n > kSortSmallCap) return;
@@ -367,6 +382,8 @@ tile_sort_gather_big_kernel(const TileWork *__restrict__ work, const unsigned *_
                             unsigned long long *__restrict__ keys, const Rec *__restrict__ rec, unsigned *__restrict__ ids_sorted,
                             Rec *__restrict__ rec_sorted) {
     extern __shared__ __align__(16) unsigned char s_sort[];
+    pdl_trigger();
+    pdl_wait();
     const unsigned nb = work->n_big;
     for (unsigned i = blockIdx.x; i < nb; i += gridDim.x)
         sort_gather_tile<kSortBigThreads, kSortBigCap, kSortBigBuckets>(ranges[big_list[i]], keys, rec, ids_sorted, rec_sorted, s_sort);

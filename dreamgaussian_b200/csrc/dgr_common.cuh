@@ -130,6 +130,13 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor grid has completed and its
+// memory is visible, pdl_trigger() lets the successor's CTAs become resident as soon as SM resources free up (they then sit in
+// pdl_wait()).  Both are no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }

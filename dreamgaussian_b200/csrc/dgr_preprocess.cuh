@@ -161,6 +161,7 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
     // added to the per-tile totals with ONE global atomic per (block, tile) — not one per instance.
     extern __shared__ unsigned s_hist[];
     __shared__ FrameConsts fc;
+    pdl_trigger();                       // the tile scan may become resident now (it waits for this grid's completion)
     load_frame(fc, viewmatrix, projmatrix, HAS_SH ? campos : nullptr);
     for (int t = threadIdx.x; t < tiles; t += kPreThreads) s_hist[t] = 0u;
     __syncthreads();

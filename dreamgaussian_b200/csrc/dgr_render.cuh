@@ -117,9 +117,11 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     const int lane = threadIdx.x & 31;
     WarpRing &rg = rings[threadIdx.x >> 5];
     RingState rs;
+    pdl_trigger();
     ring_init(rg, rs, lane);
     const float b0 = __ldg(bg), b1 = __ldg(bg + 1), b2 = __ldg(bg + 2);
     const size_t HW = (size_t)H * W;
+    pdl_wait();                          // sorted records, ranges, order, work counter
 
     // every tile is visited (heaviest first; the empty ones at the end of the order only write the background)
     for (;;) {
@@ -248,6 +250,7 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     const int lane = threadIdx.x & 31;
     WarpRing &rg = sm.ring;
     RingState rs;
+    pdl_trigger();                       // the per-Gaussian backward may take the SM resources this grid's tail frees
     ring_init(rg, rs, lane);
     const unsigned n_items = __ldcg(n_tiles_nonempty) * (unsigned)ST::kPerTile;
     const float b0 = __ldg(bg), b1 = __ldg(bg + 1), b2 = __ldg(bg + 2);

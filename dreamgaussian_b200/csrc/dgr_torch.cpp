@@ -9,6 +9,7 @@
 #include <torch/extension.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
+#include <cuda_runtime.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -51,12 +52,12 @@ std::mutex g_mu;
 std::unordered_map<uint64_t, Hint> g_hints;
 uint64_t hint_key(int dev, int64_t P, int H, int W) { return ((uint64_t)dev << 58) ^ ((uint64_t)P << 28) ^ ((uint64_t)H << 14) ^ (uint64_t)W; }
 
-struct SyncObjs { Tensor counts; void *event = nullptr; };
+struct SyncObjs { Tensor counts; void *event = nullptr; uint64_t ticket = 0; };
 SyncObjs &sync_objs(int dev) {
     thread_local std::unordered_map<int, SyncObjs> per_dev;
     SyncObjs &o = per_dev[dev];
     if (!o.event) {
-        o.counts = torch::zeros({2}, torch::dtype(torch::kInt64)).pin_memory();
+        o.counts = torch::zeros({4}, torch::dtype(torch::kInt64)).pin_memory();
         o.event = dgr_event_create();
         TORCH_CHECK(o.event, "libdgr_b200: could not create a CUDA event");
     }
@@ -125,11 +126,24 @@ forward(int64_t H, int64_t W, double tanfovx, double tanfovy, double scale_modif
     int rerun = 0;
     while (true) {
         st->binning = torch::empty({(int64_t)dgr_binning_bytes((uint64_t)cap, (int32_t)H, (int32_t)W)}, u8);
+        // ticket protocol: the scan kernel writes the counts and then the ticket into the pinned buffer; nothing but kernels
+        // goes into the stream (programmatic dependent launches chain the whole forward) and the host polls the ticket
+        const uint64_t ticket = ++so.ticket;
+        volatile uint64_t *cnt = reinterpret_cast<volatile uint64_t *>(so.counts.data_ptr<int64_t>());
         check(dgr_forward_render(&st->s, &st->g, st->geom.data_ptr(), st->binning.data_ptr(), (uint64_t)cap, st->image.data_ptr(), &out,
-                                 (big ? DGR_FLAG_BIG_TILES : 0) | rerun, reinterpret_cast<uint64_t *>(so.counts.data_ptr<int64_t>()), so.event, stream));
+                                 (big ? DGR_FLAG_BIG_TILES : 0) | rerun, reinterpret_cast<uint64_t *>(so.counts.data_ptr<int64_t>()), ticket, nullptr, stream));
         {
-            pybind11::gil_scoped_release nogil;              // the wait for the early instance-count event
-            check(dgr_event_synchronize(so.event));
+            pybind11::gil_scoped_release nogil;              // the wait for the early instance count
+            uint64_t spins = 0;
+            while (cnt[2] != ticket) {
+                if ((++spins & 0xfffff) == 0) {              // every ~1M polls: has the stream failed or finished without the ticket?
+                    const cudaError_t q = cudaStreamQuery((cudaStream_t)stream);
+                    if (q != cudaErrorNotReady && cnt[2] != ticket) {
+                        TORCH_CHECK(q == cudaSuccess, "libdgr_b200: forward failed on the device: ", cudaGetErrorString(q));
+                        TORCH_CHECK(false, "libdgr_b200: the instance count never arrived (is the count buffer device-mapped?)");
+                    }
+                }
+            }
         }
         n_inst = so.counts.data_ptr<int64_t>()[0]; n_big = so.counts.data_ptr<int64_t>()[1];
         if (n_inst <= cap && (big || n_big == 0)) break;

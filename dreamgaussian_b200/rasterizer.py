@@ -204,7 +204,7 @@ def forward_impl(rs, means3D, sh, colors_precomp, opacities, scales, rotations, 
             binning = torch.empty((lib.dgr_binning_bytes(cap, H, W),), **u8)
             _lib.check(lib.dgr_forward_render(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(geom), _ptr(binning),
                                               ctypes.c_uint64(cap), _ptr(image), ctypes.byref(out), (1 if big else 0) | rerun,
-                                              ctypes.c_void_p(n_host.data_ptr()), event, st))
+                                              ctypes.c_void_p(n_host.data_ptr()), ctypes.c_uint64(0), event, st))
             _lib.check(lib.dgr_event_synchronize(event))
             n_inst, n_big = int(n_host[0]), int(n_host[1])
             if n_inst <= cap and (big or n_big == 0):
@@ -236,7 +236,7 @@ def _host_sync_objects(dev):
         ev = _lib.load().dgr_event_create()
         if not ev:
             raise RuntimeError("libdgr_b200: could not create a CUDA event")
-        t = (torch.zeros((2,), dtype=torch.int64).pin_memory(), ctypes.c_void_p(ev))
+        t = (torch.zeros((4,), dtype=torch.int64).pin_memory(), ctypes.c_void_p(ev))
         _SYNC[key] = t
     return t
 

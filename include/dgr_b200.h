@@ -110,21 +110,27 @@ int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *ge
  * per-tile front-to-back compositing.  Nothing here waits for the host.  Two things are guessed by the caller:
  *   - `capacity_instances`, the instance capacity `binning` was sized for;
  *   - DGR_FLAG_BIG_TILES in `flags`: whether to also launch the sorter for tiles with more than 4096 instances.
- * The truth is written to geom scratch and, if counts_host != NULL (pinned host memory, 2 x uint64), copied there
- * asynchronously right after the scan: counts_host[0] = instance count, counts_host[1] = number of big tiles; if
- * count_ready_event != NULL (from dgr_event_create) it is recorded at that point, so the caller keeps enqueuing work and
- * checks the guesses once that event has fired.  If counts_host[0] > capacity_instances, or counts_host[1] > 0 without
+ * The truth is written to geom scratch and, if counts_host != NULL (pinned host memory, 4 x uint64), made available to
+ * the host right after the scan: counts_host[0] = instance count, counts_host[1] = number of big tiles.  Two protocols:
+ *   ticket == 0: an asynchronous copy, then count_ready_event (from dgr_event_create, may be NULL) is recorded — the caller
+ *                keeps enqueuing work and checks the guesses once that event has fired;
+ *   ticket != 0: the scan kernel stores the two counts and then counts_host[2] = ticket straight into the caller's memory
+ *                (which must therefore be device-mapped pinned memory — under unified addressing every cudaHostAlloc /
+ *                torch pin_memory buffer is); the caller polls counts_host[2] for the ticket value it chose for THIS call.
+ *                No copy or event sits between the kernels then, so the whole forward chains with programmatic dependent
+ *                launches (each kernel's prologue overlaps its predecessor's tail); count_ready_event is ignored.  If counts_host[0] > capacity_instances, or counts_host[1] > 0 without
  * DGR_FLAG_BIG_TILES, the call produced a memory-safe but wrong image: re-run stage 2 with corrected guesses and
  * DGR_FLAG_RERUN set. */
 #define DGR_FLAG_BIG_TILES 1
 #define DGR_FLAG_RERUN 2      /* set when stage 2 is repeated for the same stage 1 (corrected guesses) */
 int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom, void *binning,
                        uint64_t capacity_instances, void *image, const DgrImages *out, int32_t flags,
-                       uint64_t *counts_host, void *count_ready_event, void *stream);
+                       uint64_t *counts_host, uint64_t ticket, void *count_ready_event, void *stream);
 
 /* Tuning knobs (process-wide; results do not depend on them): pixels per lane of the forward / backward render
- * kernels (1, 2 or 4); tile_order bits 0-1: 0 = row-major tile issue, 1 = heaviest-first with snake order over the SMs,
- * 2 = heaviest-first plain; bit 2 (value 4) turns OFF the backward kernel's paired warp reductions (A/B switch). */
+ * kernels (1, 2 or 4; the backward has 1 and 2); tile_order: bit 3 (value 8) turns OFF programmatic dependent launches
+ * (A/B switch; the environment variable DGR_PDL=0 does the same); the other bits are accepted and ignored (the persistent
+ * render kernels always pull work heaviest tile first). */
 int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order);
 
 /* Thin cudaEvent wrappers so a host without the CUDA runtime headers (ctypes, cgo ...) can use the protocol above. */

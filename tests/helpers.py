@@ -29,6 +29,15 @@ GRAD_RTOL = 2e-3
 GRAD_ATOL = 1e-4
 GRAD_ATOL_MAX = 1e-3
 MAX_AMBIG_FRAC = 0.04
+TIE_SLACK_FACTOR = 1.5
+# float32 CUDA vs the float32 build of the oracle (compare_f32): NO decision-ambiguity exemption, only float32 depth-key
+# ties (two consecutive contributors of a pixel whose view depths differ by < 1e-6 relative: either order is a valid
+# float32 result) are set aside.  Bounds from tools/parity_report.py on B200 (profiles/r2_parity_report.json).
+F32_IMG_ATOL = 2e-4            # every non-tie pixel ...
+F32_IMG_OUTLIERS = 2e-5        # ... except this fraction of them (alpha >= 1/255 / T-stop decisions taken the other way) ...
+F32_IMG_OUTLIER_ATOL = 1e-2    # ... which stay below this
+F32_GRAD_ATOL_MAX = 3e-4       # of the tensor's scale, every non-tie Gaussian
+F32_GRAD_ATOL = 3e-5           # 99.9th percentile
 
 
 def make_case(P, res, deg, seed=0, elev=0.0, azim=0.0, opacity="trained", sigma=None, anisotropic=True, radius=2.0,
@@ -147,15 +156,20 @@ def compare(cu, ref, check_grads=True, max_ambig_frac=MAX_AMBIG_FRAC, ambig_atol
     rep["ambig_g_frac"] = float((ag != 0).mean()) if ag.size else 0.0
     if rep["ambig_px_frac"] > max_ambig_frac:
         ok = False
+    slack = TIE_SLACK_FACTOR * ref["tie_slack"].astype(np.float64) if "tie_slack" in ref else np.zeros(apx.shape)
     for name in ("color", "depth", "alpha"):
         d = np.abs(cu[name].astype(np.float64) - ref[name])
         scale = max(1.0, float(np.abs(ref[name]).max())) if name == "depth" else 1.0
         m = np.broadcast_to(apx[None], d.shape)
         clean = d[~m].max() if (~m).any() else 0.0
+        # a pixel with a float32 depth-key tie may show the other (equally valid) order: the oracle reports how far that moves
+        # the colour (sum over its ties of a1 a2 T |c1 - c2|); depth and alpha do not depend on the order of a tied pair
+        bound = ambig_atol + (np.broadcast_to(slack[None], d.shape) if name == "color" else 0.0)
+        excess = (d - bound)[m].max() if m.any() else -1.0
         amb = d[m].max() if m.any() else 0.0
         rep[name + "_err"] = float(clean / scale)
         rep[name + "_err_ambig"] = float(amb / scale)
-        if clean / scale > IMG_ATOL or amb / scale > ambig_atol:
+        if clean / scale > IMG_ATOL or excess > 0.0:
             ok = False
     rad_bad = (cu["radii"] != ref["radii"]) & ((ag & 4) == 0)
     rep["radii_mismatch"] = int(rad_bad.sum())
@@ -184,3 +198,58 @@ def compare(cu, ref, check_grads=True, max_ambig_frac=MAX_AMBIG_FRAC, ambig_atol
             if p999 > GRAD_ATOL or worst > GRAD_ATOL_MAX or worst_amb > 0.05:
                 ok = False
     return ok, rep
+
+
+def compare_f32(cu, ref32):
+    """CUDA (float32) against the float32 build of the oracle with NO decision-ambiguity exemption: only float32 depth-key
+    ties (pixels with flag bit 4; Gaussians of a tied pair or compositing in front of a material one, bits 2 | 16) are set
+    aside, and Gaussians whose radius sits on a rounding boundary (bit 4) are excused from the exact radii comparison.
+    Returns (ok, report)."""
+    rep = {}
+    ok = True
+    tie_px = (ref32["ambig_px"] & 4) != 0
+    ag = ref32["ambig_g"]
+    tie_g = (ag & (2 | 16)) != 0
+    rep["tie_px_frac"] = float(tie_px.mean()) if tie_px.size else 0.0
+    rep["tie_g_frac"] = float(tie_g.mean()) if tie_g.size else 0.0
+    for name in ("color", "depth", "alpha"):
+        d = np.abs(cu[name].astype(np.float64) - ref32[name].astype(np.float64))
+        if name == "depth":
+            d = d / max(1.0, float(np.abs(ref32[name]).max()))
+        dd = d[~np.broadcast_to(tie_px[None], d.shape)]
+        n_out = int((dd > F32_IMG_ATOL).sum())
+        rep[name + "_max"] = float(dd.max()) if dd.size else 0.0
+        rep[name + "_outliers"] = n_out
+        if n_out > max(2, int(F32_IMG_OUTLIERS * dd.size)) or (dd.size and dd.max() > F32_IMG_OUTLIER_ATOL):
+            ok = False
+    bad = (cu["radii"] != ref32["radii"]) & ((ag & 4) == 0)
+    rep["radii_mismatch"] = int(bad.sum())
+    if bad.any():
+        ok = False
+    if "grads" in ref32 and "grads" in cu:
+        floor = 1e-3 * max(float(np.abs(v).max()) if v.size else 0.0 for v in ref32["grads"].values())
+        for k, gr in ref32["grads"].items():
+            if k not in cu["grads"] or gr.size == 0:
+                continue
+            gr = gr.astype(np.float64)
+            gc = cu["grads"][k].astype(np.float64).reshape(gr.shape)
+            scale = max(float(np.abs(gr).max()), floor) or 1.0
+            e = (np.abs(gc - gr) - GRAD_RTOL * np.abs(gr)).reshape(gr.shape[0], -1).max(axis=1) / scale
+            e = e[~tie_g]
+            rep["grad_" + k] = float(e.max()) if e.size else 0.0
+            rep["grad_" + k + "_p999"] = float(np.percentile(e, 99.9)) if e.size else 0.0
+            if e.size and (e.max() > F32_GRAD_ATOL_MAX or np.percentile(e, 99.9) > F32_GRAD_ATOL):
+                ok = False
+    return ok, rep
+
+
+def report(name, **reps):
+    """Flagged fractions and deviations of a parity case: printed (pytest -s / -rP shows it) and appended to
+    gpurun_out/parity_suite.jsonl when that directory exists."""
+    import json
+    line = json.dumps({"case": name, **{k: {a: (round(b, 9) if isinstance(b, float) else b) for a, b in v.items()} for k, v in reps.items()}})
+    print(line)
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_suite.jsonl"), "a") as f:
+            f.write(line + "\n")

@@ -25,33 +25,55 @@ CASES = {
 }
 
 
+def both_oracles(name, s, i, g, max_ambig_frac=h.MAX_AMBIG_FRAC, f64=True):
+    """The rule of the suite: the CUDA result must agree (a) with the float64 oracle on everything that oracle does not flag
+    as a decision a float32 implementation may take differently, and (b) with the float32 oracle with NO such exemption —
+    only float32 depth-key ties are set aside there."""
+    cu = h.run_cuda(s, i, g)
+    ok32, rep32 = h.compare_f32(cu, h.run_oracle(s, i, g, dtype=np.float32))
+    if f64:
+        ok64, rep64 = h.compare(cu, h.run_oracle(s, i, g), max_ambig_frac=max_ambig_frac)
+    else:
+        ok64, rep64 = True, {}
+    h.report(name, vs_f64=rep64, vs_f32=rep32)
+    assert ok64, ("float64 oracle", rep64)
+    assert ok32, ("float32 oracle", rep32)
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_forward_backward_parity(name):
     s, i = h.make_case(**CASES[name])
-    g = h.upstream_grads(s["image_height"], s["image_width"])
-    ref = h.run_oracle(s, i, g)
-    cu = h.run_cuda(s, i, g)
-    ok, rep = h.compare(cu, ref)
-    assert ok, rep
+    both_oracles(name, s, i, h.upstream_grads(s["image_height"], s["image_width"]))
 
 
 def test_cfg2_full_size_parity():
     """BASELINE.json configs[1]: 100k Gaussians, 800x800, SH degree 3, forward + backward."""
     s, i = h.make_case(P=100000, res=800, deg=3)
-    g = h.upstream_grads(800, 800)
-    ok, rep = h.compare(h.run_cuda(s, i, g), h.run_oracle(s, i, g))
-    assert ok, rep
+    both_oracles("cfg2_100k_800", s, i, h.upstream_grads(800, 800))
 
 
-def test_cfg3_view_full_size_parity_against_the_float32_oracle():
+def test_cfg2_at_the_reference_initial_opacity_full_size_parity():
+    """configs[1] with every opacity at the reference's initial 0.1 (gs_renderer.py:346): no early termination, every list is
+    walked to its end.  8 % of the pixels sit within float32 reach of the alpha >= 1/255 contour of some Gaussian (each
+    Gaussian's footprint ends on that contour at o = 0.1), hence the larger allowance for flagged pixels against float64."""
+    s, i = h.make_case(P=100000, res=800, deg=3, opacity="init")
+    both_oracles("cfg2_100k_800_init", s, i, h.upstream_grads(800, 800), max_ambig_frac=0.12)
+
+
+def test_cfg3_view_full_size_parity():
     """One view of BASELINE.json configs[2] (500k Gaussians, 512x512, SH degree 3; ~2000-entry pixel lists, big-tile sorter).
-    Against the float64 oracle this shape shows float32 depth-key ties (flagged pixels off by up to 0.05, a few gradient
-    outliers at 4e-3 of scale — and the float32 CPU oracle shows the SAME numbers to six digits, profiles/r1_extra_parity.json),
-    so the yardstick here is the float32 build of the oracle, with the suite's normal bounds."""
+    Float32 depth keys tie between consecutive contributors here: the float64 comparison allows a tied pixel the colour shift
+    of its ties (oracle tie_slack) and sets aside the Gaussians compositing in front of a material tie (flag bit 16)."""
     s, i = h.make_case(P=500000, res=512, deg=3, sigma=0.0075, elev=-12, azim=75)
-    g = h.upstream_grads(512, 512, depth=False)
-    ok, rep = h.compare(h.run_cuda(s, i, g), h.run_oracle(s, i, g, dtype=np.float32))
-    assert ok, rep
+    both_oracles("cfg3_view_500k_512", s, i, h.upstream_grads(512, 512, depth=False))
+
+
+def test_cfg5_full_size_parity_against_the_float32_oracle():
+    """BASELINE.json configs[4]: 2M Gaussians, 1600x1600, SH degree 3 (14 M tile instances, big-tile sorter on most tiles),
+    forward + backward against the float32 oracle (the float64 one adds nothing here: the deviations between the two CPU
+    builds at this depth complexity are float32 depth-key ties)."""
+    s, i = h.make_case(P=2000000, res=1600, deg=3, sigma=0.595 * 2000000 ** (-1.0 / 3.0), elev=10, azim=30)
+    both_oracles("cfg5_2M_1600", s, i, h.upstream_grads(1600, 1600, depth=False), f64=False)
 
 
 def test_equal_depths_resolve_by_index_like_the_reference():

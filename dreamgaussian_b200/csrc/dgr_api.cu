@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <utility>
@@ -192,7 +193,7 @@ __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched
 
 // tuning knobs (dgr_set_tuning): pixels per lane of the render kernels, heaviest-first tile order on/off.  Atomics: any host
 // thread may change them while another launches (each launch reads every knob once).
-std::atomic<int> g_ppl_fwd{1}, g_ppl_bwd{2};
+std::atomic<int> g_ppl_fwd{1}, g_ppl_bwd{2}, g_u_fwd{0}, g_u_bwd{0};      // u = 0: the default batching of that sub-tile shape
 std::atomic<bool> g_no_order{false};
 
 using SmS = SortSmem<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>;
@@ -203,22 +204,14 @@ using SmB = SortSmem<kSortBigThreads, kSortBigCap, kSortBigBuckets>;
 struct DevInfo {
     bool ready = false;
     int sms = 148;
-    int fwd_grid[3] = {0, 0, 0};      // persistent grid of render_fwd_kernel<1|2|4>
-    int bwd_grid[2] = {0, 0};         // persistent grid of render_bwd_kernel<1|2>
     int big_grid = 148;               // big-tile sorter: one CTA per SM
+    std::map<const void *, int> grids;   // persistent (occupancy x SMs) grid of every render kernel instantiation used so far
 };
 constexpr int kMaxDevices = 64;
 DevInfo g_dev[kMaxDevices];
 std::mutex g_dev_mu;
 
-template <class K>
-int persistent_grid(K kernel, int threads, size_t smem, int sms) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    return per_sm * sms;
-}
-
-const DevInfo *dev_info() {
+DevInfo *dev_info() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { fail(-1, "cudaGetDevice failed or device ordinal above 63"); return nullptr; }
     std::lock_guard<std::mutex> lock(g_dev_mu);
@@ -230,17 +223,24 @@ const DevInfo *dev_info() {
     cudaError_t e = cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sort_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmS::bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sort_gather_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmB::bytes);
-    const size_t b1 = sizeof(BwdSmem<1>) * kRenderWarps, b2 = sizeof(BwdSmem<2>) * kRenderWarps;
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(render_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(render_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2);
     if (e != cudaSuccess) { fail((int)e, "cudaFuncSetAttribute", cudaGetErrorString(e)); return nullptr; }
-    d.fwd_grid[0] = persistent_grid(render_fwd_kernel<1>, kRenderThreads, 0, d.sms);
-    d.fwd_grid[1] = persistent_grid(render_fwd_kernel<2>, kRenderThreads, 0, d.sms);
-    d.fwd_grid[2] = persistent_grid(render_fwd_kernel<4>, kRenderThreads, 0, d.sms);
-    d.bwd_grid[0] = persistent_grid(render_bwd_kernel<1>, kRenderThreads, b1, d.sms);
-    d.bwd_grid[1] = persistent_grid(render_bwd_kernel<2>, kRenderThreads, b2, d.sms);
     d.ready = true;
     return &d;
+}
+
+// persistent grid of a render kernel on the current device: (CTAs that fit on one SM) x SMs, computed once per (device, kernel)
+template <class K>
+int persistent_grid(DevInfo *d, K kernel, int threads, size_t smem) {
+    std::lock_guard<std::mutex> lock(g_dev_mu);
+    const void *key = reinterpret_cast<const void *>(kernel);
+    auto it = d->grids.find(key);
+    if (it != d->grids.end()) return it->second;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int g = per_sm * d->sms;
+    d->grids[key] = g;
+    return g;
 }
 }  // namespace
 
@@ -278,6 +278,8 @@ int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order) {
     g_ppl_fwd = ppl_fwd; g_ppl_bwd = ppl_bwd == 4 ? 2 : ppl_bwd;          // the backward has 8x4 and 8x8 sub-tiles
     g_no_order = (tile_order & 3) == 0;
     g_pdl = (tile_order & 8) ? 0 : 1;                   // bit 3: programmatic dependent launches OFF (A/B switch)
+    g_u_fwd = (tile_order >> 4) & 7;                    // bits 4-6 / 8-10: hits evaluated together by the forward / backward
+    g_u_bwd = (tile_order >> 8) & 7;                    // render kernels (1, 2 or 4; 0 = default of the sub-tile shape)
     return 0;
 }
 
@@ -343,7 +345,7 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
     unsigned *tile_order = reinterpret_cast<unsigned *>(image + IL.off_order);
     unsigned *big_list = reinterpret_cast<unsigned *>(image + IL.off_biglist);
     TileWork *work = reinterpret_cast<TileWork *>(image + IL.off_work);
-    const DevInfo *dv = dev_info();
+    DevInfo *dv = dev_info();
     if (!dv) return -1;
     (void)(flags & DGR_FLAG_RERUN);           // a re-run only repeats the scan from the (still valid) per-tile totals
     DGR_KERNEL("tile_scan", st, s->debug,
@@ -369,13 +371,19 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
                                 (const unsigned *)big_list, (const uint2 *)ranges, keys, rec, ids, recs));
     }
     // persistent forward render: every (tile, sub-tile) is a work item, handed out heaviest tile first
-    const int ppl = g_ppl_fwd.load();
-#define DGR_RENDER_FWD(PPL_, GRID_)                                                                             \
-    DGR_KERNEL("render_fwd", st, s->debug,                                                                      \
-               launch_k(render_fwd_kernel<PPL_>, dim3((unsigned)min(GRID_, (tiles * SubTile<PPL_>::kPerTile + kRenderWarps - 1) / kRenderWarps)),   \
-                        dim3(kRenderThreads), 0, st, true, H, W, IL.gx, (const unsigned *)tile_order, (unsigned)(tiles * SubTile<PPL_>::kPerTile),       \
-                        &work->fwd_next, (const uint2 *)ranges, (const Rec *)recs, s->bg, out->color, out->depth, out->alpha, n_contrib, final_T))
-    if (ppl == 4) DGR_RENDER_FWD(4, dv->fwd_grid[2]); else if (ppl == 2) DGR_RENDER_FWD(2, dv->fwd_grid[1]); else DGR_RENDER_FWD(1, dv->fwd_grid[0]);
+    const int ppl = g_ppl_fwd.load(), uf = g_u_fwd.load();
+#define DGR_RENDER_FWD(PPL_, U_)                                                                                \
+    do {                                                                                                        \
+        const int items_ = tiles * SubTile<PPL_>::kPerTile;                                                     \
+        const int grid_ = min(persistent_grid(dv, render_fwd_kernel<PPL_, U_>, kRenderThreads, 0), (items_ + kRenderWarps - 1) / kRenderWarps); \
+        DGR_KERNEL("render_fwd", st, s->debug,                                                                  \
+                   launch_k(render_fwd_kernel<PPL_, U_>, dim3((unsigned)grid_), dim3(kRenderThreads), 0, st, true, H, W, IL.gx,   \
+                            (const unsigned *)tile_order, (unsigned)items_, &work->fwd_next, (const uint2 *)ranges, (const Rec *)recs, \
+                            s->bg, out->color, out->depth, out->alpha, n_contrib, final_T));                     \
+    } while (0)
+    if (ppl == 4) { if (uf == 2) DGR_RENDER_FWD(4, 2); else DGR_RENDER_FWD(4, 1); }
+    else if (ppl == 2) { if (uf == 1) DGR_RENDER_FWD(2, 1); else if (uf == 4) DGR_RENDER_FWD(2, 4); else DGR_RENDER_FWD(2, 2); }
+    else { if (uf == 1) DGR_RENDER_FWD(1, 1); else if (uf == 2) DGR_RENDER_FWD(1, 2); else DGR_RENDER_FWD(1, 4); }
 #undef DGR_RENDER_FWD
     return 0;
 }
@@ -402,21 +410,26 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
     // one memset: the work counter of the persistent backward render kernel + the per-Gaussian moment accumulators
     DGR_CUDA(cudaMemsetAsync(geom + GL.off_bwdwork, 0, (GL.off_gradrec - GL.off_bwdwork) + (size_t)g->P * kGradRecFloats * 4, st));
     if (binning && capacity > 0) {
-        const DevInfo *dv = dev_info();
+        DevInfo *dv = dev_info();
         if (!dv) return -1;
         const TileWork *work = reinterpret_cast<const TileWork *>(image + IL.off_work);
         unsigned *bwd_next = reinterpret_cast<unsigned *>(geom + GL.off_bwdwork);
-        const int ppl = g_ppl_bwd.load();
-#define DGR_RENDER_BWD(PPL_, GRID_)                                                                                           \
-    DGR_KERNEL("render_bwd", st, s->debug,                                                                                 \
-               render_bwd_kernel<PPL_><<<(unsigned)min(GRID_, (tiles * SubTile<PPL_>::kPerTile + kRenderWarps - 1) / kRenderWarps), kRenderThreads, \
-                                         sizeof(BwdSmem<PPL_>) * kRenderWarps, st>>>(                                          \
-                   H, W, IL.gx, reinterpret_cast<const unsigned *>(image + IL.off_order), &work->n_nonempty, bwd_next,     \
-                   reinterpret_cast<const uint2 *>(image + IL.off_ranges),                                                 \
-                   reinterpret_cast<const Rec *>(binning + BL.off_rec), reinterpret_cast<const unsigned *>(binning + BL.off_ids), \
-                   s->bg, reinterpret_cast<const float *>(image + IL.off_finalT),                                          \
-                   reinterpret_cast<const unsigned *>(image + IL.off_ncontrib), gin->dL_dcolor, gin->dL_ddepth, gin->dL_dalpha, grad_rec))
-        if (ppl == 1) DGR_RENDER_BWD(1, dv->bwd_grid[0]); else DGR_RENDER_BWD(2, dv->bwd_grid[1]);
+        const int ppl = g_ppl_bwd.load(), ub = g_u_bwd.load();
+#define DGR_RENDER_BWD(PPL_, U_)                                                                                              \
+    do {                                                                                                                   \
+        const size_t smem_ = sizeof(BwdSmem<PPL_>) * kRenderWarps;                                                         \
+        const int grid_ = min(persistent_grid(dv, render_bwd_kernel<PPL_, U_>, kRenderThreads, smem_),                     \
+                              (tiles * SubTile<PPL_>::kPerTile + kRenderWarps - 1) / kRenderWarps);                        \
+        DGR_KERNEL("render_bwd", st, s->debug,                                                                             \
+                   launch_k(render_bwd_kernel<PPL_, U_>, dim3((unsigned)grid_), dim3(kRenderThreads), smem_, st, false, H, W, IL.gx, \
+                            reinterpret_cast<const unsigned *>(image + IL.off_order), &work->n_nonempty, bwd_next,         \
+                            reinterpret_cast<const uint2 *>(image + IL.off_ranges),                                        \
+                            reinterpret_cast<const Rec *>(binning + BL.off_rec), reinterpret_cast<const unsigned *>(binning + BL.off_ids), \
+                            s->bg, reinterpret_cast<const float *>(image + IL.off_finalT),                                 \
+                            reinterpret_cast<const unsigned *>(image + IL.off_ncontrib), gin->dL_dcolor, gin->dL_ddepth, gin->dL_dalpha, grad_rec)); \
+    } while (0)
+        if (ppl == 1) { if (ub == 1) DGR_RENDER_BWD(1, 1); else if (ub == 4) DGR_RENDER_BWD(1, 4); else DGR_RENDER_BWD(1, 2); }
+        else { if (ub == 1) DGR_RENDER_BWD(2, 1); else if (ub == 4) DGR_RENDER_BWD(2, 4); else DGR_RENDER_BWD(2, 2); }
 #undef DGR_RENDER_BWD
     }
     DGR_KERNEL("preprocess_bwd", st, s->debug, DGR_DISPATCH(launch_pre_bwd, s, g, radii, reinterpret_cast<const unsigned *>(geom + GL.off_touched), grad_rec, gout, st));
@@ -434,7 +447,7 @@ int dgr_peer_allreduce(const uint64_t *peer_ptrs, int32_t world, int32_t rank, u
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n4 = (size_t)(n_floats / 4);
     if (n4 == 0 || world == 1) return 0;
-    const DevInfo *dv = dev_info();
+    DevInfo *dv = dev_info();
     if (!dv) return -1;
     const size_t per = (n4 + world - 1) / world;
     int grid = (int)((per + 512 * kUnroll - 1) / (512 * kUnroll));

@@ -105,7 +105,10 @@ struct RenderWork {                      // lives in image scratch (TileWork) / 
 // ----------------------------------------------------------------------------------------------------------------
 // Forward.
 // ----------------------------------------------------------------------------------------------------------------
-template <int PPL>
+// U = hits evaluated together: the alpha of a (pixel, record) pair does not depend on the compositing state, so the long
+// part of the dependent chain (shared-memory read -> quadratic form -> ex2) of U hitting records is in flight at once and
+// only the short T / colour update runs in sequence.  Same per-pixel operation order for every U: bit-identical images.
+template <int PPL, int U>
 __global__ void __launch_bounds__(kRenderThreads)
 render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, unsigned n_items,
                   unsigned *__restrict__ work_next, const uint2 *__restrict__ ranges,
@@ -164,28 +167,48 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
             if (lane < cnt) hit = record_hits_subtile(rg.rec[s][lane], wx0, wx1, wy0, wy1);
             unsigned mask = __ballot_sync(0xffffffffu, hit);
             while (mask) {
-                const int j = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const Rec *r = &rg.rec[s][j];
-                const float4 q0 = r->q0, q1 = r->q1;
-                float4 q2;
-                bool have_q2 = false;
+                int js[U];
+                int nh = 0;
 #pragma unroll
-                for (int p = 0; p < PPL; p++) {
-                    const float dx = q0.x - fx[p], dy = q0.y - fy[p];
-                    const float p2 = eval_power2(q0, q1, dx, dy);
-                    const float ag = __fmul_rn(q1.y, ex2_approx(p2));
-                    const float a = fminf(DGR_ALPHA_MAX, ag);
-                    bool ok = (!done[p]) & (p2 <= 0.f) & (a >= DGR_ALPHA_MIN);
-                    const float test_T = __fmul_rn(T[p], 1.f - a);
-                    if (ok && test_T < DGR_T_STOP) { done[p] = true; ok = false; }
-                    if (ok) {
-                        if (!have_q2) { q2 = r->q2; have_q2 = true; }
-                        const float w = __fmul_rn(a, T[p]);
-                        C0[p] = __fmaf_rn(q2.x, w, C0[p]); C1[p] = __fmaf_rn(q2.y, w, C1[p]); C2[p] = __fmaf_rn(q2.z, w, C2[p]);
-                        D[p] = __fmaf_rn(q1.z, w, D[p]);
-                        T[p] = test_T;
-                        last[p] = (unsigned)(c * kChunk + j + 1);
+                for (int u = 0; u < U; u++) {
+                    js[u] = 0;
+                    if (mask) { js[u] = __ffs(mask) - 1; mask &= mask - 1; nh = u + 1; }
+                }
+                float av[U][PPL], dep[U], cr[U], cg[U], cb[U];
+                bool pre[U][PPL];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (u < nh) {
+                        const Rec *r = &rg.rec[s][js[u]];
+                        const float4 q0 = r->q0, q1 = r->q1, q2 = r->q2;
+                        dep[u] = q1.z; cr[u] = q2.x; cg[u] = q2.y; cb[u] = q2.z;
+#pragma unroll
+                        for (int p = 0; p < PPL; p++) {
+                            const float dx = q0.x - fx[p], dy = q0.y - fy[p];
+                            const float p2 = eval_power2(q0, q1, dx, dy);
+                            const float ag = __fmul_rn(q1.y, ex2_approx(p2));
+                            av[u][p] = fminf(DGR_ALPHA_MAX, ag);
+                            pre[u][p] = (p2 <= 0.f) & (av[u][p] >= DGR_ALPHA_MIN);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (u < nh) {
+#pragma unroll
+                        for (int p = 0; p < PPL; p++) {
+                            const float a = av[u][p];
+                            bool ok = (!done[p]) & pre[u][p];
+                            const float test_T = __fmul_rn(T[p], 1.f - a);
+                            if (ok && test_T < DGR_T_STOP) { done[p] = true; ok = false; }
+                            if (ok) {
+                                const float w = __fmul_rn(a, T[p]);
+                                C0[p] = __fmaf_rn(cr[u], w, C0[p]); C1[p] = __fmaf_rn(cg[u], w, C1[p]); C2[p] = __fmaf_rn(cb[u], w, C2[p]);
+                                D[p] = __fmaf_rn(dep[u], w, D[p]);
+                                T[p] = test_T;
+                                last[p] = (unsigned)(c * kChunk + js[u] + 1);
+                            }
+                        }
                     }
                 }
             }
@@ -232,7 +255,9 @@ struct BwdSmem {
     float4 g[kPix];                                         // per pixel: dL/dC rgb, dL/dD
 };
 
-template <int PPL>
+// U = hitting records whose alpha / skip decisions (all independent of the traversal state) are evaluated together before
+// the short sequential T / R updates: shortens the dependent chain of a warp that walks a long list.
+template <int PPL, int U>
 __global__ void __launch_bounds__(kRenderThreads)
 render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const unsigned *__restrict__ n_tiles_nonempty,
                   unsigned *__restrict__ work_next, const uint2 *__restrict__ ranges,
@@ -364,44 +389,60 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
             if (lane < cnt) hit = record_hits_subtile(rg.rec[s][lane], wx0, wx1, wy0, wy1);
             unsigned mask = __ballot_sync(0xffffffffu, hit);
             while (mask) {
-                const int j = 31 - __clz(mask);
-                mask &= ~(1u << j);
-                const Rec *r = &rg.rec[s][j];
-                const float4 q0 = r->q0, q1 = r->q1;
-                const unsigned gidx = (unsigned)(c * kChunk + j);
-                float dxv[PPL], dyv[PPL], agv[PPL], av[PPL];
-                bool okv[PPL];
-                bool any_ok = false;
+                int js[U];
+                int nh = 0;
 #pragma unroll
-                for (int p = 0; p < PPL; p++) {
-                    dxv[p] = q0.x - fx[p]; dyv[p] = q0.y - fy[p];
-                    const float p2 = eval_power2(q0, q1, dxv[p], dyv[p]);
-                    agv[p] = __fmul_rn(q1.y, ex2_approx(p2));
-                    av[p] = fminf(DGR_ALPHA_MAX, agv[p]);
-                    okv[p] = (gidx < last[p]) & (p2 <= 0.f) & (av[p] >= DGR_ALPHA_MIN);
-                    any_ok = any_ok || okv[p];
+                for (int u = 0; u < U; u++) {
+                    js[u] = 0;
+                    if (mask) { js[u] = 31 - __clz(mask); mask &= ~(1u << js[u]); nh = u + 1; }
                 }
-                if (!__any_sync(0xffffffffu, any_ok)) continue;
-                const float4 q2 = r->q2;
-                float *row = &sm.uw[nslots][0];
+                float agv[U][PPL], av[U][PPL], rcx[U], rcy[U], dep[U], cr[U], cg[U], cb[U];
+                bool okv[U][PPL], any_ok[U];
 #pragma unroll
-                for (int p = 0; p < PPL; p++) {
-                    float u = 0.f, w = 0.f;
-                    if (okv[p]) {
-                        const float ir = rcp_approx(1.f - av[p]);
-                        T[p] = T[p] * ir;
-                        const float sdot = __fmaf_rn(q2.x, gc0[p], __fmaf_rn(q2.y, gc1[p], __fmaf_rn(q2.z, gc2[p], __fmaf_rn(q1.z, gd[p], ga[p]))));
-                        const float dL_da = T[p] * sdot - R[p] * ir;
-                        w = av[p] * T[p];
-                        R[p] = __fmaf_rn(w, sdot, R[p]);
-                        u = agv[p] * dL_da;
+                for (int u = 0; u < U; u++) {
+                    any_ok[u] = false;
+                    if (u < nh) {
+                        const Rec *r = &rg.rec[s][js[u]];
+                        const float4 q0 = r->q0, q1 = r->q1, q2 = r->q2;
+                        const unsigned gidx = (unsigned)(c * kChunk + js[u]);
+                        rcx[u] = q0.x - (float)wx0; rcy[u] = q0.y - (float)wy0; dep[u] = q1.z; cr[u] = q2.x; cg[u] = q2.y; cb[u] = q2.z;
+                        bool mine = false;
+#pragma unroll
+                        for (int p = 0; p < PPL; p++) {
+                            const float dx = q0.x - fx[p], dy = q0.y - fy[p];
+                            const float p2 = eval_power2(q0, q1, dx, dy);
+                            agv[u][p] = __fmul_rn(q1.y, ex2_approx(p2));
+                            av[u][p] = fminf(DGR_ALPHA_MAX, agv[u][p]);
+                            okv[u][p] = (gidx < last[p]) & (p2 <= 0.f) & (av[u][p] >= DGR_ALPHA_MIN);
+                            mine = mine || okv[u][p];
+                        }
+                        any_ok[u] = __any_sync(0xffffffffu, mine);
                     }
-                    *reinterpret_cast<float2 *>(row + 2 * (p * 32 + lane)) = make_float2(u, w);
                 }
-                const unsigned id_j = __shfl_sync(0xffffffffu, my_id, j);
-                if (lane == nslots) { cap_cx = q0.x - (float)wx0; cap_cy = q0.y - (float)wy0; cap_id = id_j; }
-                nslots++;
-                if (nslots == kBatch) flush();
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (u < nh && any_ok[u]) {
+                        float *row = &sm.uw[nslots][0];
+#pragma unroll
+                        for (int p = 0; p < PPL; p++) {
+                            float uu = 0.f, w = 0.f;
+                            if (okv[u][p]) {
+                                const float ir = rcp_approx(1.f - av[u][p]);
+                                T[p] = T[p] * ir;
+                                const float sdot = __fmaf_rn(cr[u], gc0[p], __fmaf_rn(cg[u], gc1[p], __fmaf_rn(cb[u], gc2[p], __fmaf_rn(dep[u], gd[p], ga[p]))));
+                                const float dL_da = T[p] * sdot - R[p] * ir;
+                                w = av[u][p] * T[p];
+                                R[p] = __fmaf_rn(w, sdot, R[p]);
+                                uu = agv[u][p] * dL_da;
+                            }
+                            *reinterpret_cast<float2 *>(row + 2 * (p * 32 + lane)) = make_float2(uu, w);
+                        }
+                        const unsigned id_j = __shfl_sync(0xffffffffu, my_id, js[u]);
+                        if (lane == nslots) { cap_cx = rcx[u]; cap_cy = rcy[u]; cap_id = id_j; }
+                        nslots++;
+                        if (nslots == kBatch) flush();
+                    }
+                }
             }
             __syncwarp();                                       // every lane has left stage s
             if (rs.issued < nchunks) {

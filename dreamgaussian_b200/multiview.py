@@ -67,6 +67,8 @@ class ViewShardedRasterizer:
         self.collective = "none"
         self._hdl = None
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        if os.environ.get("DGR_NO_PEER") == "1":          # A/B switch: plain NCCL all_reduce instead of the library's kernels
+            peer_allreduce = False
         if multi and peer_allreduce and self.device.type == "cuda":
             # the gradient buffer in symmetric memory + this library's NVLink all-reduce kernel; NCCL is the fallback
             try:

@@ -36,7 +36,9 @@ TIE_SLACK_FACTOR = 1.5
 F32_IMG_ATOL = 2e-4            # every non-tie pixel ...
 F32_IMG_OUTLIERS = 2e-5        # ... except this fraction of them (alpha >= 1/255 / T-stop decisions taken the other way) ...
 F32_IMG_OUTLIER_ATOL = 1e-2    # ... which stay below this
-F32_GRAD_ATOL_MAX = 3e-4       # of the tensor's scale, every non-tie Gaussian
+F32_GRAD_ATOL_MAX = 3e-4       # of the tensor's scale, every non-tie Gaussian ...
+F32_GRAD_OUTLIERS = 2e-4       # ... except this fraction of them (a Gaussian whose footprint edge crosses a pixel at alpha = 1/255
+F32_GRAD_OUTLIER_ATOL = 2e-2   #     exactly where the two float32 evaluations of exp differ) which stay below this
 F32_GRAD_ATOL = 3e-5           # 99.9th percentile
 
 
@@ -238,7 +240,10 @@ def compare_f32(cu, ref32):
             e = e[~tie_g]
             rep["grad_" + k] = float(e.max()) if e.size else 0.0
             rep["grad_" + k + "_p999"] = float(np.percentile(e, 99.9)) if e.size else 0.0
-            if e.size and (e.max() > F32_GRAD_ATOL_MAX or np.percentile(e, 99.9) > F32_GRAD_ATOL):
+            n_out = int((e > F32_GRAD_ATOL_MAX).sum())
+            rep["grad_" + k + "_outliers"] = n_out
+            if e.size and (n_out > max(2, int(F32_GRAD_OUTLIERS * e.size)) or e.max() > F32_GRAD_OUTLIER_ATOL
+                           or np.percentile(e, 99.9) > F32_GRAD_ATOL):
                 ok = False
     return ok, rep
 

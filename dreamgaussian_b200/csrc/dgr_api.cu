@@ -305,8 +305,8 @@ int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *ge
     GeomLayout L(g->P, s->image_height, s->image_width);
     ImageLayout IL(s->image_height, s->image_width);
     if ((size_t)L.tiles * 4 > kMaxTileSmem) return fail(-3, "image has more than 51200 tiles (16x16): not supported");
-    // one memset: the work block + the per-tile instance totals the preprocess kernel adds into
-    DGR_CUDA(cudaMemsetAsync(image + IL.off_work, 0, (IL.off_count - IL.off_work) + (size_t)L.tiles * 4, st));
+    // one memset: the work block + the per-tile instance totals the preprocess kernel adds into + the per-tile run cursors
+    DGR_CUDA(cudaMemsetAsync(image + IL.off_work, 0, (IL.off_cursor - IL.off_work) + (size_t)L.tiles * 4, st));
     if (g->P > 0) {
         if (!radii) return fail(-1, "radii is NULL");
         DGR_KERNEL("preprocess_fwd", st, s->debug, DGR_DISPATCH(launch_pre_fwd, s, g, radii, geom, L, reinterpret_cast<unsigned *>(image + IL.off_count), st));
@@ -348,20 +348,24 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
     DevInfo *dv = dev_info();
     if (!dv) return -1;
     (void)(flags & DGR_FLAG_RERUN);           // a re-run only repeats the scan from the (still valid) per-tile totals
-    DGR_KERNEL("tile_scan", st, s->debug,
-               launch_k(tile_scan_kernel, dim3(1), dim3(1024), 0, st, true, tiles, (const unsigned *)tile_count, (unsigned long long)capacity, ranges,
-                        tile_cursor, hdr, tile_order, work, big_list, (volatile unsigned long long *)(ticket ? counts_host : nullptr),
-                        (unsigned long long)ticket));
+    if (flags & DGR_FLAG_RERUN)         // the run reservations start from zero again (the per-tile totals are still valid)
+        DGR_CUDA(cudaMemsetAsync(tile_cursor, 0, (size_t)tiles * 4, st));
+    {
+        // instance emission; its extra block publishes ranges / order / counts (capacity 0: only that block has work to do)
+        const size_t smem = (size_t)tiles * 4;
+        const int nb = (g->P > 0 && capacity > 0) ? GL.nblocks : 0;
+        DGR_KERNEL("emit_instances", st, s->debug,
+                   launch_k(emit_instances_kernel, dim3(nb + 1), dim3(kPreThreads), smem, st, !(flags & DGR_FLAG_RERUN), g->P, IL.gx, tiles, GL.iters, nb, rec,
+                            reinterpret_cast<const unsigned *>(geom + GL.off_touched), (const unsigned *)tile_count, (unsigned long long)capacity,
+                            tile_cursor, keys, ranges, hdr, tile_order, work, big_list,
+                            (volatile unsigned long long *)(ticket ? counts_host : nullptr), (unsigned long long)ticket));
+    }
     if (!ticket) {            // copy + event between the kernels (this also ends the chain of programmatic dependent launches here)
         if (counts_host)      // { n_instances, n_big_tiles }
             DGR_CUDA(cudaMemcpyAsync(counts_host, geom, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         if (count_ready_event) DGR_CUDA(cudaEventRecord((cudaEvent_t)count_ready_event, st));
     }
     if (g->P > 0 && capacity > 0) {
-        const size_t smem = (size_t)tiles * 4;
-        DGR_KERNEL("emit_instances", st, s->debug,
-                   launch_k(emit_instances_kernel, dim3(GL.nblocks), dim3(kPreThreads), smem, st, true, g->P, IL.gx, tiles, GL.iters, rec,
-                            reinterpret_cast<const unsigned *>(geom + GL.off_touched), (const uint2 *)ranges, tile_cursor, keys));
         DGR_KERNEL("tile_sort_gather", st, s->debug,
                    launch_k(tile_sort_gather_kernel, dim3(tiles), dim3(kSortSmallThreads), SmS::bytes, st, true, (const unsigned *)tile_order,
                             (const uint2 *)ranges, keys, rec, ids, recs));

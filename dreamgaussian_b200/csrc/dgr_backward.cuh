@@ -76,7 +76,7 @@ __device__ __forceinline__ void store_sh_grads(float *__restrict__ dL_dshs, int 
 }
 
 template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
-__global__ void __launch_bounds__(kPreThreads, 4)
+__global__ void __launch_bounds__(kPreThreads, 2)
 preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, float scale_modifier,
                       const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
                       const float *__restrict__ campos,
@@ -96,7 +96,30 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const bool acc = accumulate != 0;
     const bool in_range = g < P;
-    const bool visible = in_range && radii[g] > 0;
+    // every input of this Gaussian is requested up front (one memory round trip; none of it depends on the backward render)
+    int radius_in = 0;
+    unsigned touched_in = 0;
+    float3 p = make_float3(0.f, 0.f, 0.f), s_in = make_float3(0.f, 0.f, 0.f);
+    float4 q_in = make_float4(1.f, 0.f, 0.f, 0.f);
+    float o_in = 0.f, S6[6], shc[48];
+    if (in_range) {
+        radius_in = radii[g];
+        touched_in = __ldg(touched + g);
+        p = make_float3(__ldg(means3D + 3 * (size_t)g), __ldg(means3D + 3 * (size_t)g + 1), __ldg(means3D + 3 * (size_t)g + 2));
+        if (HAS_COV) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) S6[i] = __ldg(cov3D_precomp + 6 * (size_t)g + i);
+        } else {
+            s_in = make_float3(__ldg(scales + 3 * (size_t)g), __ldg(scales + 3 * (size_t)g + 1), __ldg(scales + 3 * (size_t)g + 2));
+            q_in = ldg_f4(rotations + 4 * (size_t)g);
+        }
+        o_in = __ldg(opacities + g);
+        if (HAS_SH) {
+            if (RAW) { if (DEG > 0) load_sh_row<DEG, 1>(shs_rest + (size_t)g * (M - 1) * 3, ((M - 1) & 3) == 0, shc); }       // d basis_0 = 0
+            else load_sh_row<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, shc);
+        }
+    }
+    const bool visible = in_range && radius_in > 0;
     float bs[16];
     float gr[3] = { 0.f, 0.f, 0.f };
 #pragma unroll
@@ -112,20 +135,15 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
         if (HAS_COV && dL_dcov3D) { for (int k = 0; k < 6; k++) dL_dcov3D[6 * (size_t)g + k] = 0.f; }
     }
     if (visible) {
-        const float3 p = make_float3(__ldg(means3D + 3 * (size_t)g), __ldg(means3D + 3 * (size_t)g + 1), __ldg(means3D + 3 * (size_t)g + 2));
-        float S6[6];
         float R[9];
         float3 s = make_float3(0.f, 0.f, 0.f);
         float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
         float inv_qnorm = 1.f;
-        if (HAS_COV) {
-#pragma unroll
-            for (int i = 0; i < 6; i++) S6[i] = __ldg(cov3D_precomp + 6 * (size_t)g + i);
-        } else {
-            s = make_float3(__ldg(scales + 3 * (size_t)g), __ldg(scales + 3 * (size_t)g + 1), __ldg(scales + 3 * (size_t)g + 2));
+        if (!HAS_COV) {
+            s = s_in;
             if (RAW) s = make_float3(expf(s.x), expf(s.y), expf(s.z));
             s = make_float3(scale_modifier * s.x, scale_modifier * s.y, scale_modifier * s.z);
-            q = ldg_f4(rotations + 4 * (size_t)g);
+            q = q_in;
             if (RAW) q = act_normalize(q, inv_qnorm);
             quat_to_R(q, R);
             cov3d_from_scale_rot(s, R, S6);
@@ -136,7 +154,7 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
         const float a = geo.cxx, b = geo.cxy, c = geo.cyy;
         const float det = a * c - b * b, di = 1.f / det;
         const float cA = c * di, cB = -b * di, cC = a * di;
-        const float o = RAW ? act_sigmoid(__ldg(opacities + g)) : __ldg(opacities + g);
+        const float o = RAW ? act_sigmoid(o_in) : o_in;
 
         // Everything above reads only the op's inputs: under a programmatic dependent launch it overlaps the tail of the
         // backward render kernel.  The moments that kernel accumulates are complete after this point.
@@ -164,7 +182,7 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
         // xyz_gradient_accum += |d L / d means2D[:, :2]| of THIS render, denom += 1, max_radii2D = max(max_radii2D, radii)
         if (xyz_gradient_accum) xyz_gradient_accum[g] += sqrtf(gndx * gndx + gndy * gndy);
         if (denom) denom[g] += 1.f;
-        if (max_radii2D) max_radii2D[g] = fmaxf(max_radii2D[g], (float)radii[g]);
+        if (max_radii2D) max_radii2D[g] = fmaxf(max_radii2D[g], (float)radius_in);
         {
             const float *PM = fc.PM;
             const float mul1 = geo.ndcx * geo.pw, mul2 = geo.ndcy * geo.pw;     // ph.x * pw^2, ph.y * pw^2
@@ -181,17 +199,19 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
             const float il = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
             dx *= il; dy *= il; dz *= il;
             sh_basis<DEG>(dx, dy, dz, bs);
-            const unsigned flags = __ldg(touched + g) >> 29;              // SH channels the forward clamped at 0
+            const unsigned flags = touched_in >> 29;                     // SH channels the forward clamped at 0
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) gr[ch] = ((flags >> ch) & 1u) ? 0.f : g_rgb[ch];
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-            auto dir_grad = [&](int k, float c0, float c1, float c2) {
-                const float dotc = c0 * gr[0] + c1 * gr[1] + c2 * gr[2];
+            constexpr int NB = (DEG + 1) * (DEG + 1);
+#pragma unroll
+            for (int k = 1; k < NB; k++) {                                // d basis_0 = 0
+                const int off = RAW ? 3 * (k - 1) : 3 * k;
+                const float dotc = shc[off] * gr[0] + shc[off + 1] * gr[1] + shc[off + 2] * gr[2];
                 float bx, by, bz;
                 sh_dbasis(k, dx, dy, dz, bx, by, bz);
-                ddx += bx * dotc; ddy += by * dotc; ddz += bz * dotc; };
-            if (RAW) { if (DEG > 0) for_each_sh_coeff<DEG, 1>(shs_rest + (size_t)g * (M - 1) * 3, ((M - 1) & 3) == 0, dir_grad); }   // d basis_0 = 0
-            else for_each_sh_coeff<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, dir_grad);
+                ddx += bx * dotc; ddy += by * dotc; ddz += bz * dotc;
+            }
             const float dot = dx * ddx + dy * ddy + dz * ddz;
             dmean[0] += (ddx - dx * dot) * il; dmean[1] += (ddy - dy * dot) * il; dmean[2] += (ddz - dz * dot) * il;
         } else if (dL_dcolors) {

@@ -4,11 +4,13 @@
 // and reads the instance count back to the host.  Here:
 //   1. the preprocess kernel histograms the instances of each block of Gaussians per tile in shared memory and adds the
 //      block's counts to the per-tile totals (one global atomic per touched (block, tile), not per instance);
-//   2. tile_scan_kernel turns the totals into per-tile [start, end) ranges (clipped to the buffer capacity), publishes the
-//      instance count, the heaviest-first issue order and the big-tile list — all on the device, no host round trip;
-//   3. emit_instances_kernel counts its block's instances per tile again (shared memory), reserves a contiguous run of
-//      each touched tile's range with ONE global atomic, and appends (depth bits << 32 | Gaussian id) keys there with
-//      shared-memory cursors.  The order inside a tile is arbitrary at this point;
+//   2. emit_instances_kernel counts its block's instances per tile again (shared memory), scans the per-tile totals itself
+//      for the range starts, reserves a contiguous run of each touched tile's range with ONE global atomic, and appends
+//      (depth bits << 32 | Gaussian id) keys there with shared-memory cursors — the order inside a tile is arbitrary at
+//      this point.  One extra block of the same launch publishes what everybody else needs: per-tile [start, end) ranges
+//      (clipped to the buffer capacity), the instance count (device + pinned host memory, no host round trip), the
+//      heaviest-first issue order and the big-tile list;
+//   3. (there is no separate scan kernel);
 //   4. tile_sort_gather_kernel sorts each tile's segment by (depth, id) in shared memory (keys are unique, so the result
 //      is deterministic and identical to the reference's stable (tile, depth) order) and, in the same pass, gathers the
 //      48-byte records into depth-sorted, per-tile contiguous order for the bulk-TMA staging of the render kernels.
@@ -80,25 +82,26 @@ __device__ __forceinline__ int order_bin(unsigned count) {
     return max(0, kOrderBins - 2 - cls);
 }
 
-// One CTA: exclusive scan of the per-tile instance counts -> ranges (clipped to `cap`), total -> header; plus the
-// heaviest-first issue order of the render kernels (counting sort on log-scale population classes — longest
-// processing time first keeps the big tiles off the tail) and the list of tiles too big for the per-tile sort CTA.
-// One CTA of 1024 threads.  Every thread owns kScanTPT consecutive tiles in registers (up to 8192 tiles in one pass, more
-// in further passes): one global read of the counts, one block scan, then ranges / issue order / big-tile list.
+// Tile metadata for the kernels that follow (one CTA of NT threads): exclusive scan of the per-tile instance counts ->
+// ranges (clipped to `cap`), total -> header (+ the caller's pinned host memory); the heaviest-first issue order of the
+// persistent render kernels (counting sort on log-scale population classes) with the empty tiles at its tail; the list of
+// tiles too big for the per-tile sort CTA.  Every thread owns kScanTPT consecutive tiles in registers per pass.
 constexpr int kScanTPT = 8;
 
+template <int NT>
 __device__ __forceinline__ void
-tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long long cap, uint2 *__restrict__ ranges,
-              unsigned *__restrict__ tile_cursor, GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order,
-              TileWork *__restrict__ work, unsigned *__restrict__ big_list) {
+tile_meta_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long long cap, uint2 *__restrict__ ranges,
+              GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order, TileWork *__restrict__ work,
+              unsigned *__restrict__ big_list, volatile unsigned long long *counts_host, unsigned long long ticket) {
+    constexpr int NW = NT / 32;
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_carry, s_total;
     __shared__ unsigned s_bin[kOrderBins], s_nbig, s_nne;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) { s_carry = 0; s_nbig = 0; s_nne = 0; }
-    if (tid < kOrderBins) s_bin[tid] = 0;
+    for (int i = tid; i < kOrderBins; i += NT) s_bin[i] = 0;
     __syncthreads();
-    const int span = 1024 * kScanTPT;
+    const int span = NT * kScanTPT;
     for (int base = 0; base < tiles; base += span) {
         unsigned cnt[kScanTPT];
         unsigned long long sum = 0;
@@ -111,7 +114,7 @@ tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
         if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
         if (warp == 0) {
-            const unsigned long long w = s_warp[lane];
+            const unsigned long long w = lane < NW ? s_warp[lane] : 0ull;
             unsigned long long winc = w;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += n; }
@@ -128,13 +131,12 @@ tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
                 const unsigned long long s = run < cap ? run : cap;
                 const unsigned long long e = (run + cnt[j]) < cap ? (run + cnt[j]) : cap;
                 ranges[t0 + j] = make_uint2((unsigned)s, (unsigned)e);
-                tile_cursor[t0 + j] = (unsigned)s;                            // emit reserves runs of the range from here
                 pop = (unsigned)(e - s);                                      // clipped population
                 bin = order_bin(pop);
                 if (pop > (unsigned)kSortSmallCap) big_list[atomicAdd(&s_nbig, 1u)] = (unsigned)(t0 + j);
             }
-            // Neighbouring tiles fall into the same population class (and 60 % of all tiles are empty): one shared-memory
-            // atomic per (warp, class) instead of one per tile — the per-tile version serialised ~1500 atomics on one address.
+            // Neighbouring tiles fall into the same population class (and most tiles of a centred object are empty): one
+            // shared-memory atomic per (warp, class) — one per tile serialised ~1500 atomics on the "empty" class.
             const unsigned same = __match_any_sync(0xffffffffu, bin);
             if (bin >= 0 && lane == __ffs(same) - 1) atomicAdd(&s_bin[bin], (unsigned)__popc(same));
             const unsigned nz = __ballot_sync(0xffffffffu, pop > 0u);
@@ -145,7 +147,17 @@ tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
         if (tid == 0) s_carry += s_total;
         __syncthreads();
     }
-    if (tid == 0) { hdr->n_inst = s_carry; hdr->n_big = s_nbig; work->n_big = s_nbig; work->n_nonempty = s_nne; work->fwd_next = 0u; }
+    if (tid == 0) {
+        hdr->n_inst = s_carry; hdr->n_big = s_nbig; work->n_big = s_nbig; work->n_nonempty = s_nne; work->fwd_next = 0u;
+        // The host wants the instance count early (is the caller's capacity guess large enough?).  With a ticket the counts
+        // go straight into the caller's pinned, device-mapped host memory: no copy or event between the kernels, the forward
+        // chains with programmatic dependent launches while the host polls the ticket.
+        if (counts_host && ticket) {
+            counts_host[0] = s_carry; counts_host[1] = s_nbig;
+            __threadfence_system();
+            counts_host[2] = ticket;
+        }
+    }
     // counting sort of the tiles by population class (heaviest first)
     if (warp == 0) {
         unsigned run = 0;
@@ -161,7 +173,7 @@ tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
     __syncthreads();
     // Plain descending order: the render kernels are persistent and pull work items from this list through an atomic
     // counter (longest processing time first); the empty tiles form its tail (class kOrderBins - 1).
-    for (int t0 = 0; t0 < tiles; t0 += 1024) {
+    for (int t0 = 0; t0 < tiles; t0 += NT) {
         const int t = t0 + tid;
         int bin = -1;
         if (t < tiles) { const uint2 r = ranges[t]; bin = order_bin(r.y - r.x); }
@@ -174,41 +186,36 @@ tile_scan_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
     }
 }
 
-// One CTA.  (Re-run with a larger capacity when the caller's guess was too small: the totals in tile_count stay valid.)
-__global__ void __launch_bounds__(1024)
-tile_scan_kernel(int tiles, const unsigned *__restrict__ tile_count, unsigned long long cap, uint2 *__restrict__ ranges,
-                 unsigned *__restrict__ tile_cursor, GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order,
-                 TileWork *__restrict__ work, unsigned *__restrict__ big_list,
-                 volatile unsigned long long *counts_host, unsigned long long ticket) {
-    pdl_trigger();
-    pdl_wait();                          // the per-tile totals of the preprocess kernel are complete
-    tile_scan_cta(tiles, tile_count, cap, ranges, tile_cursor, hdr, tile_order, work, big_list);
-    // The host wants the instance count early (is the caller's capacity guess large enough?).  With a ticket the counts go
-    // straight into the caller's pinned, device-mapped host memory — no copy or event between this kernel and the next, so
-    // the rest of the forward chains behind it with programmatic dependent launches while the host polls the ticket.
-    if (counts_host && ticket && threadIdx.x == 0) {
-        counts_host[0] = hdr->n_inst; counts_host[1] = hdr->n_big;
-        __threadfence_system();
-        counts_host[2] = ticket;
-    }
-}
+// Instance emission, same block <-> Gaussian mapping as the preprocess kernel; grid = nblocks + 1.
+//   blocks 0 .. nblocks-1:  pass 1 counts the block's instances per tile in shared memory; the block then scans the per-tile
+//     totals itself (every thread owns a run of consecutive tiles; the totals are 4 B x tiles, L2-resident) and every
+//     touched tile reserves a contiguous run of its range with ONE global atomic on the tile's (zero-initialised) cursor —
+//     the atomics of a thread are issued back to back, 8 in flight; pass 2 appends the keys at the reserved position +
+//     (shared-memory atomic rank).  Positions at or beyond the instance capacity are dropped.
+//   block nblocks:  the tile metadata the later kernels and the host need (tile_meta_cta).  There is no separate scan kernel.
+constexpr int kEmitBatch = 8;
 
-// Same block <-> Gaussian mapping as the preprocess kernel.  Pass 1 counts the block's instances per tile in shared
-// memory; every touched tile then reserves a contiguous run [base, base + count) of its range with one global atomic on
-// the tile's cursor; pass 2 appends the keys at base + (shared-memory atomic rank).  Runs beyond the (capacity-clipped)
-// range end are dropped.
 __global__ void __launch_bounds__(kPreThreads)
-emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, const Rec *__restrict__ rec, const unsigned *__restrict__ touched,
-                      const uint2 *__restrict__ ranges, unsigned *__restrict__ tile_cursor,
-                      unsigned long long *__restrict__ keys) {
+emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, int nblocks, const Rec *__restrict__ rec, const unsigned *__restrict__ touched,
+                      const unsigned *__restrict__ tile_count, unsigned long long cap, unsigned *__restrict__ tile_cursor,
+                      unsigned long long *__restrict__ keys, uint2 *__restrict__ ranges, GeomHeader *__restrict__ hdr,
+                      unsigned *__restrict__ tile_order, TileWork *__restrict__ work, unsigned *__restrict__ big_list,
+                      volatile unsigned long long *counts_host, unsigned long long ticket) {
     extern __shared__ unsigned s_off[];
+    __shared__ unsigned long long s_part[kPreThreads / 32];
     pdl_trigger();
-    for (int t = threadIdx.x; t < tiles; t += kPreThreads) s_off[t] = 0u;
-    pdl_wait();                          // ranges / cursors of the tile scan (and, transitively, the preprocess outputs)
+    if ((int)blockIdx.x == nblocks) {
+        pdl_wait();                      // the per-tile totals of the preprocess kernel are complete
+        tile_meta_cta<kPreThreads>(tiles, tile_count, cap, ranges, hdr, tile_order, work, big_list, counts_host, ticket);
+        return;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int t = tid; t < tiles; t += kPreThreads) s_off[t] = 0u;
+    pdl_wait();                          // records, touched counts and per-tile totals of the preprocess kernel
     __syncthreads();
     // pass 1: per-tile counts of this block (the same AABB walk as the preprocess histogram)
     for (int it = 0; it < gpb_iters; it++) {
-        const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + threadIdx.x);
+        const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + tid);
         if (g >= P) continue;
         const int cnt = (int)(__ldg(touched + g) & 0x1fffffffu);
         if (cnt == 0) continue;
@@ -222,15 +229,39 @@ emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, const Rec *__rest
             if (x == tw) { x = 0; t += gx - tw; }
         }
     }
-    __syncthreads();
-    for (int t = threadIdx.x; t < tiles; t += kPreThreads) {
-        const unsigned c = s_off[t];
-        if (c) s_off[t] = atomicAdd(tile_cursor + t, c);
+    // range starts: exclusive scan of the per-tile totals; thread i owns tiles [i K, (i + 1) K)
+    const int K = (tiles + kPreThreads - 1) / kPreThreads;
+    const int t_lo = min(tiles, tid * K), t_hi = min(tiles, t_lo + K);
+    unsigned long long sum = 0;
+    for (int t = t_lo; t < t_hi; t++) sum += __ldcg(tile_count + t);
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+    if (lane == 31) s_part[warp] = inc;
+    __syncthreads();                     // (also: pass 1 is complete)
+    unsigned long long run = inc - sum;
+    for (int w = 0; w < warp; w++) run += s_part[w];
+    // reservation: s_off[t] = range start + run of this block inside the tile
+    for (int t0 = t_lo; t0 < t_hi; t0 += kEmitBatch) {
+        unsigned c[kEmitBatch], got[kEmitBatch];
+        unsigned long long start[kEmitBatch];
+#pragma unroll
+        for (int j = 0; j < kEmitBatch; j++) {
+            const int t = t0 + j;
+            c[j] = 0u; start[j] = 0ull;
+            if (t < t_hi) { c[j] = s_off[t]; start[j] = run < cap ? run : cap; run += __ldcg(tile_count + t); }
+        }
+#pragma unroll
+        for (int j = 0; j < kEmitBatch; j++) got[j] = c[j] ? atomicAdd(tile_cursor + t0 + j, c[j]) : 0u;
+#pragma unroll
+        for (int j = 0; j < kEmitBatch; j++)
+            if (c[j]) s_off[t0 + j] = (unsigned)start[j] + got[j];
     }
     __syncthreads();
     // pass 2: append
+    const unsigned cap32 = (unsigned)cap;
     for (int it = 0; it < gpb_iters; it++) {
-        const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + threadIdx.x);
+        const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + tid);
         if (g >= P) continue;
         const int cnt = (int)(__ldg(touched + g) & 0x1fffffffu);                  // = tw * th (same AABB as the histogram)
         if (cnt == 0) continue;
@@ -243,7 +274,7 @@ emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, const Rec *__rest
 #pragma unroll 4
         for (int i = 0; i < cnt; i++) {
             const unsigned pos = atomicAdd(&s_off[t], 1u);
-            if (pos < __ldg(&ranges[t].y)) keys[pos] = key;               // beyond the (clipped) range: dropped
+            if (pos < cap32) keys[pos] = key;                             // beyond the instance capacity: dropped
             x++; t++;
             if (x == tw) { x = 0; t += gx - tw; }
         }

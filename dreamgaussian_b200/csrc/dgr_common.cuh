@@ -74,9 +74,9 @@ struct GeomLayout {
     }
 };
 
-// image scratch: [work 256][tile_count u32 x tiles][ranges uint2 x tiles][tile_cursor u32 x tiles][tile_order u32 x tiles]
+// image scratch: [work 256][tile_count u32 x tiles][tile_cursor u32 x tiles][ranges uint2 x tiles][tile_order u32 x tiles]
 //                [big_list u32 x tiles][n_contrib u32 x HW][final_T f32 x HW]
-// (work + tile_count are adjacent: the forward zeroes both with ONE memset before the preprocess kernel adds into tile_count)
+// (work, tile_count and tile_cursor are adjacent: the forward zeroes them with ONE memset before the preprocess kernel)
 struct ImageLayout {
     size_t off_ranges, off_count, off_cursor, off_order, off_biglist, off_work, off_ncontrib, off_finalT, total;
     int gx, gy;
@@ -87,8 +87,8 @@ struct ImageLayout {
         size_t o = 0;
         off_work = o;     o = align_up(o + 256, 256);
         off_count = o;    o = align_up(o + tiles * 4, 256);
-        off_ranges = o;   o = align_up(o + tiles * 8, 256);
         off_cursor = o;   o = align_up(o + tiles * 4, 256);
+        off_ranges = o;   o = align_up(o + tiles * 8, 256);
         off_order = o;    o = align_up(o + tiles * 4, 256);
         off_biglist = o;  o = align_up(o + tiles * 4, 256);
         off_ncontrib = o; o = align_up(o + hw * 4, 256);

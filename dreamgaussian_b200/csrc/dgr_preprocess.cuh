@@ -94,6 +94,28 @@ __device__ __forceinline__ void for_each_sh_coeff(const float *row, bool vec, F 
     }
 }
 
+// One Gaussian's whole SH row ([M][3] layout, coefficients FIRST .. NB-1) into registers: 128-bit loads when the row is
+// 16-byte aligned (M % 4 == 0: the deg-1 and deg-3 tensors), scalar loads otherwise.  Used at the very top of the
+// per-Gaussian kernels, together with every other input of the Gaussian, so that ONE memory round trip feeds the thread
+// (these kernels run 2-3 CTAs per SM at 100k Gaussians: latency, not registers, is what limits them).
+template <int DEG, int FIRST = 0>
+__device__ __forceinline__ void load_sh_row(const float *row, bool vec, float (&c)[48]) {
+    constexpr int N = 3 * ((DEG + 1) * (DEG + 1) - FIRST);
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < (N + 3) / 4; i++) {
+            const float4 v = ldg_f4(row + 4 * i);
+            c[4 * i] = v.x;
+            if (4 * i + 1 < 48) c[4 * i + 1] = v.y;
+            if (4 * i + 2 < 48) c[4 * i + 2] = v.z;
+            if (4 * i + 3 < 48) c[4 * i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) c[i] = __ldg(row + i);
+    }
+}
+
 // GaussianModel activations (gs_renderer.py:127-138, :196-216), applied in registers when the caller passes the raw
 // parameters (DgrGaussians.activations): scaling = exp, opacity = sigmoid, rotation = F.normalize (eps 1e-12).
 __device__ __forceinline__ float act_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
@@ -147,7 +169,7 @@ __device__ __forceinline__ void project_geo(const FrameConsts &fc, const float3 
 }
 
 template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
-__global__ void __launch_bounds__(kPreThreads, 4)
+__global__ void __launch_bounds__(kPreThreads, 2)
 preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, float scale_modifier,
                       const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
                       const float *__restrict__ campos,
@@ -172,18 +194,35 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
         int radius_out = 0;
         Rec r;
         r.q0 = make_float4(0.f, 0.f, 0.f, 0.f); r.q1 = r.q0; r.q2 = r.q0;
+        // every input of this Gaussian is requested before anything is computed (one memory round trip)
         const float3 p = make_float3(__ldg(means3D + 3 * (size_t)g), __ldg(means3D + 3 * (size_t)g + 1), __ldg(means3D + 3 * (size_t)g + 2));
+        float S6[6];
+        float3 s_in = make_float3(0.f, 0.f, 0.f);
+        float4 q_in = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (HAS_COV) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) S6[i] = __ldg(cov3D_precomp + 6 * (size_t)g + i);
+        } else {
+            s_in = make_float3(__ldg(scales + 3 * (size_t)g), __ldg(scales + 3 * (size_t)g + 1), __ldg(scales + 3 * (size_t)g + 2));
+            q_in = ldg_f4(rotations + 4 * (size_t)g);
+        }
+        const float o_in = __ldg(opacities + g);
+        float shc[48], dc0 = 0.f, dc1 = 0.f, dc2 = 0.f, pc0 = 0.f, pc1 = 0.f, pc2 = 0.f;
+        if (HAS_SH) {
+            if (RAW) {          // _features_dc [P,1,3] + _features_rest [P,M-1,3]: no torch.cat copy
+                dc0 = __ldg(shs + 3 * (size_t)g); dc1 = __ldg(shs + 3 * (size_t)g + 1); dc2 = __ldg(shs + 3 * (size_t)g + 2);
+                if (DEG > 0) load_sh_row<DEG, 1>(shs_rest + (size_t)g * (M - 1) * 3, ((M - 1) & 3) == 0, shc);
+            } else load_sh_row<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, shc);
+        } else {
+            pc0 = __ldg(colors_precomp + 3 * (size_t)g); pc1 = __ldg(colors_precomp + 3 * (size_t)g + 1); pc2 = __ldg(colors_precomp + 3 * (size_t)g + 2);
+        }
         const float tzc = p.x * fc.V[2] + p.y * fc.V[6] + p.z * fc.V[10] + fc.V[14];
         if (tzc > DGR_NEAR_CULL_Z) {
-            float S6[6];
-            if (HAS_COV) {
-#pragma unroll
-                for (int i = 0; i < 6; i++) S6[i] = __ldg(cov3D_precomp + 6 * (size_t)g + i);
-            } else {
-                float3 s = make_float3(__ldg(scales + 3 * (size_t)g), __ldg(scales + 3 * (size_t)g + 1), __ldg(scales + 3 * (size_t)g + 2));
+            if (!HAS_COV) {
+                float3 s = s_in;
                 if (RAW) s = make_float3(expf(s.x), expf(s.y), expf(s.z));
                 s = make_float3(scale_modifier * s.x, scale_modifier * s.y, scale_modifier * s.z);
-                float4 q = ldg_f4(rotations + 4 * (size_t)g);
+                float4 q = q_in;
                 if (RAW) { float inv; q = act_normalize(q, inv); }
                 float R[9]; quat_to_R(q, R);
                 cov3d_from_scale_rot(s, R, S6);
@@ -208,7 +247,7 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                 const int rmaxy = min(gy, max(0, (int)((my + rad_f + (kTile - 1)) / kTile)));
                 if (rmaxx > rminx && rmaxy > rminy) {
                     radius_out = (int)rad_f;
-                    const float o = RAW ? act_sigmoid(__ldg(opacities + g)) : __ldg(opacities + g);
+                    const float o = RAW ? act_sigmoid(o_in) : o_in;
                     // colour
                     float cr, cg, cb;
                     if (HAS_SH) {
@@ -216,21 +255,22 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                         const float il = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
                         dx *= il; dy *= il; dz *= il;
                         float b[16]; sh_basis<DEG>(dx, dy, dz, b);
-                        cr = 0.f; cg = 0.f; cb = 0.f;
-                        if (RAW) {          // _features_dc [P,1,3] + _features_rest [P,M-1,3]: no torch.cat copy
-                            cr = b[0] * __ldg(shs + 3 * (size_t)g); cg = b[0] * __ldg(shs + 3 * (size_t)g + 1); cb = b[0] * __ldg(shs + 3 * (size_t)g + 2);
-                            if (DEG > 0)
-                                for_each_sh_coeff<DEG, 1>(shs_rest + (size_t)g * (M - 1) * 3, ((M - 1) & 3) == 0, [&](int k, float c0, float c1, float c2) {
-                                    cr += b[k] * c0; cg += b[k] * c1; cb += b[k] * c2; });
-                        } else
-                        for_each_sh_coeff<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, [&](int k, float c0, float c1, float c2) {
-                            cr += b[k] * c0; cg += b[k] * c1; cb += b[k] * c2; });
+                        constexpr int NB = (DEG + 1) * (DEG + 1);
+                        if (RAW) {
+                            cr = b[0] * dc0; cg = b[0] * dc1; cb = b[0] * dc2;
+#pragma unroll
+                            for (int k = 1; k < NB; k++) { cr += b[k] * shc[3 * (k - 1)]; cg += b[k] * shc[3 * (k - 1) + 1]; cb += b[k] * shc[3 * (k - 1) + 2]; }
+                        } else {
+                            cr = 0.f; cg = 0.f; cb = 0.f;
+#pragma unroll
+                            for (int k = 0; k < NB; k++) { cr += b[k] * shc[3 * k]; cg += b[k] * shc[3 * k + 1]; cb += b[k] * shc[3 * k + 2]; }
+                        }
                         cr += DGR_SH_OFFSET; cg += DGR_SH_OFFSET; cb += DGR_SH_OFFSET;
                         // channels clamped at 0 get no colour gradient: remembered in the top bits of `touched`
                         clamp_flags = (cr < 0.f ? 1u : 0u) | (cg < 0.f ? 2u : 0u) | (cb < 0.f ? 4u : 0u);
                         cr = fmaxf(cr, 0.f); cg = fmaxf(cg, 0.f); cb = fmaxf(cb, 0.f);
                     } else {
-                        cr = __ldg(colors_precomp + 3 * (size_t)g); cg = __ldg(colors_precomp + 3 * (size_t)g + 1); cb = __ldg(colors_precomp + 3 * (size_t)g + 2);
+                        cr = pc0; cg = pc1; cb = pc2;
                     }
                     const float di = 1.f / det;
                     const float cA = geo.cyy * di, cB = -geo.cxy * di, cC = geo.cxx * di;

@@ -136,6 +136,7 @@ constexpr size_t kMaxTileSmem = 200 * 1024;      // tile-histogram rows live in 
 template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
 void launch_pre_fwd(const DgrSettings *s, const DgrGaussians *g, int *radii, char *geom, const GeomLayout &L, unsigned *tile_count,
                     cudaStream_t st) {
+    unsigned *run_matrix = reinterpret_cast<unsigned *>(geom + L.off_runs);
     const size_t smem = (size_t)L.tiles * 4;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -143,7 +144,7 @@ void launch_pre_fwd(const DgrSettings *s, const DgrGaussians *g, int *radii, cha
         g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
         s->campos, g->means3D, g->shs, g->shs_rest, g->colors_precomp, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii,
         reinterpret_cast<Rec *>(geom + L.off_rec), reinterpret_cast<unsigned *>(geom + L.off_touched),
-        tile_count, L.tiles, L.iters);
+        tile_count, run_matrix, L.tiles, L.iters);
 }
 
 template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
@@ -305,8 +306,8 @@ int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *ge
     GeomLayout L(g->P, s->image_height, s->image_width);
     ImageLayout IL(s->image_height, s->image_width);
     if ((size_t)L.tiles * 4 > kMaxTileSmem) return fail(-3, "image has more than 51200 tiles (16x16): not supported");
-    // one memset: the work block + the per-tile instance totals the preprocess kernel adds into + the per-tile run cursors
-    DGR_CUDA(cudaMemsetAsync(image + IL.off_work, 0, (IL.off_cursor - IL.off_work) + (size_t)L.tiles * 4, st));
+    // one memset: the work block + the per-tile instance totals the preprocess kernel adds into
+    DGR_CUDA(cudaMemsetAsync(image + IL.off_work, 0, (IL.off_count - IL.off_work) + (size_t)L.tiles * 4, st));
     if (g->P > 0) {
         if (!radii) return fail(-1, "radii is NULL");
         DGR_KERNEL("preprocess_fwd", st, s->debug, DGR_DISPATCH(launch_pre_fwd, s, g, radii, geom, L, reinterpret_cast<unsigned *>(image + IL.off_count), st));
@@ -333,7 +334,7 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
     if ((size_t)tiles * 4 > kMaxTileSmem) return fail(-3, "image has more than 51200 tiles (16x16): not supported");
     uint2 *ranges = reinterpret_cast<uint2 *>(image + IL.off_ranges);
     unsigned *tile_count = reinterpret_cast<unsigned *>(image + IL.off_count);
-    unsigned *tile_cursor = reinterpret_cast<unsigned *>(image + IL.off_cursor);
+    const unsigned *run_matrix = reinterpret_cast<const unsigned *>(geom + GL.off_runs);
     unsigned *n_contrib = reinterpret_cast<unsigned *>(image + IL.off_ncontrib);
     float *final_T = reinterpret_cast<float *>(image + IL.off_finalT);
     GeomHeader *hdr = reinterpret_cast<GeomHeader *>(geom);
@@ -348,16 +349,15 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
     DevInfo *dv = dev_info();
     if (!dv) return -1;
     (void)(flags & DGR_FLAG_RERUN);           // a re-run only repeats the scan from the (still valid) per-tile totals
-    if (flags & DGR_FLAG_RERUN)         // the run reservations start from zero again (the per-tile totals are still valid)
-        DGR_CUDA(cudaMemsetAsync(tile_cursor, 0, (size_t)tiles * 4, st));
+    // (a re-run with corrected guesses repeats everything from here: per-tile totals and run matrix are still valid)
     {
         // instance emission; its extra block publishes ranges / order / counts (capacity 0: only that block has work to do)
         const size_t smem = (size_t)tiles * 4;
         const int nb = (g->P > 0 && capacity > 0) ? GL.nblocks : 0;
         DGR_KERNEL("emit_instances", st, s->debug,
-                   launch_k(emit_instances_kernel, dim3(nb + 1), dim3(kPreThreads), smem, st, !(flags & DGR_FLAG_RERUN), g->P, IL.gx, tiles, GL.iters, nb, rec,
+                   launch_k(emit_instances_kernel, dim3(nb + 1), dim3(kPreThreads), smem, st, true, g->P, IL.gx, tiles, GL.iters, nb, rec,
                             reinterpret_cast<const unsigned *>(geom + GL.off_touched), (const unsigned *)tile_count, (unsigned long long)capacity,
-                            tile_cursor, keys, ranges, hdr, tile_order, work, big_list,
+                            run_matrix, keys, ranges, hdr, tile_order, work, big_list,
                             (volatile unsigned long long *)(ticket ? counts_host : nullptr), (unsigned long long)ticket));
     }
     if (!ticket) {            // copy + event between the kernels (this also ends the chain of programmatic dependent launches here)

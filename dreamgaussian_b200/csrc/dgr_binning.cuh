@@ -3,11 +3,11 @@
 // The reference op sorts ALL (tile, depth) keys with one device-wide 64-bit radix sort (6 passes over N_inst pairs)
 // and reads the instance count back to the host.  Here:
 //   1. the preprocess kernel histograms the instances of each block of Gaussians per tile in shared memory and adds the
-//      block's counts to the per-tile totals (one global atomic per touched (block, tile), not per instance);
-//   2. emit_instances_kernel counts its block's instances per tile again (shared memory), scans the per-tile totals itself
-//      for the range starts, reserves a contiguous run of each touched tile's range with ONE global atomic, and appends
-//      (depth bits << 32 | Gaussian id) keys there with shared-memory cursors — the order inside a tile is arbitrary at
-//      this point.  One extra block of the same launch publishes what everybody else needs: per-tile [start, end) ranges
+//      block's counts to the per-tile totals: one global atomic per touched (block, tile), not per instance, and what the
+//      atomic returns is where the block's run starts inside the tile (kept in a [blocks x tiles] run matrix);
+//   2. emit_instances_kernel scans the per-tile totals itself for the range starts, adds its row of the run matrix and
+//      appends (depth bits << 32 | Gaussian id) keys there with shared-memory cursors — the order inside a tile is
+//      arbitrary at this point.  One extra block of the same launch publishes what everybody else needs: per-tile [start, end) ranges
 //      (clipped to the buffer capacity), the instance count (device + pinned host memory, no host round trip), the
 //      heaviest-first issue order and the big-tile list;
 //   3. (there is no separate scan kernel);
@@ -187,48 +187,26 @@ tile_meta_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
 }
 
 // Instance emission, same block <-> Gaussian mapping as the preprocess kernel; grid = nblocks + 1.
-//   blocks 0 .. nblocks-1:  pass 1 counts the block's instances per tile in shared memory; the block then scans the per-tile
-//     totals itself (every thread owns a run of consecutive tiles; the totals are 4 B x tiles, L2-resident) and every
-//     touched tile reserves a contiguous run of its range with ONE global atomic on the tile's (zero-initialised) cursor —
-//     the atomics of a thread are issued back to back, 8 in flight; pass 2 appends the keys at the reserved position +
-//     (shared-memory atomic rank).  Positions at or beyond the instance capacity are dropped.
+//   blocks 0 .. nblocks-1:  the block scans the per-tile totals itself for the range starts (every thread owns a run of
+//     consecutive tiles; the totals are 4 B x tiles, L2-resident), adds its row of the run matrix (where the preprocess
+//     kernel's reservation put this block inside each tile) and appends the keys at that position + (shared-memory atomic
+//     rank): ONE shared-memory atomic and one 8-byte store per instance.  Positions at or beyond the capacity are dropped.
 //   block nblocks:  the tile metadata the later kernels and the host need (tile_meta_cta).  There is no separate scan kernel.
-constexpr int kEmitBatch = 8;
-
 __global__ void __launch_bounds__(kPreThreads)
 emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, int nblocks, const Rec *__restrict__ rec, const unsigned *__restrict__ touched,
-                      const unsigned *__restrict__ tile_count, unsigned long long cap, unsigned *__restrict__ tile_cursor,
+                      const unsigned *__restrict__ tile_count, unsigned long long cap, const unsigned *__restrict__ run_matrix,
                       unsigned long long *__restrict__ keys, uint2 *__restrict__ ranges, GeomHeader *__restrict__ hdr,
                       unsigned *__restrict__ tile_order, TileWork *__restrict__ work, unsigned *__restrict__ big_list,
                       volatile unsigned long long *counts_host, unsigned long long ticket) {
     extern __shared__ unsigned s_off[];
     __shared__ unsigned long long s_part[kPreThreads / 32];
     pdl_trigger();
+    pdl_wait();                          // records, touched counts, per-tile totals and run matrix of the preprocess kernel
     if ((int)blockIdx.x == nblocks) {
-        pdl_wait();                      // the per-tile totals of the preprocess kernel are complete
         tile_meta_cta<kPreThreads>(tiles, tile_count, cap, ranges, hdr, tile_order, work, big_list, counts_host, ticket);
         return;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int t = tid; t < tiles; t += kPreThreads) s_off[t] = 0u;
-    pdl_wait();                          // records, touched counts and per-tile totals of the preprocess kernel
-    __syncthreads();
-    // pass 1: per-tile counts of this block (the same AABB walk as the preprocess histogram)
-    for (int it = 0; it < gpb_iters; it++) {
-        const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + tid);
-        if (g >= P) continue;
-        const int cnt = (int)(__ldg(touched + g) & 0x1fffffffu);
-        if (cnt == 0) continue;
-        const unsigned ax = __float_as_uint(__ldg(&rec[g].q1.w)), ay = __float_as_uint(__ldg(&rec[g].q2.w));
-        const int tx0 = (int)(ax & 0xffffu) >> 4, tw = ((int)(ax >> 16) >> 4) - tx0 + 1;
-        const int ty0 = (int)(ay & 0xffffu) >> 4;
-        int x = 0, t = ty0 * gx + tx0;
-        for (int i = 0; i < cnt; i++) {
-            atomicAdd(&s_off[t], 1u);
-            x++; t++;
-            if (x == tw) { x = 0; t += gx - tw; }
-        }
-    }
     // range starts: exclusive scan of the per-tile totals; thread i owns tiles [i K, (i + 1) K)
     const int K = (tiles + kPreThreads - 1) / kPreThreads;
     const int t_lo = min(tiles, tid * K), t_hi = min(tiles, t_lo + K);
@@ -238,27 +216,16 @@ emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, int nblocks, cons
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
     if (lane == 31) s_part[warp] = inc;
-    __syncthreads();                     // (also: pass 1 is complete)
+    __syncthreads();
     unsigned long long run = inc - sum;
     for (int w = 0; w < warp; w++) run += s_part[w];
-    // reservation: s_off[t] = range start + run of this block inside the tile
-    for (int t0 = t_lo; t0 < t_hi; t0 += kEmitBatch) {
-        unsigned c[kEmitBatch], got[kEmitBatch];
-        unsigned long long start[kEmitBatch];
-#pragma unroll
-        for (int j = 0; j < kEmitBatch; j++) {
-            const int t = t0 + j;
-            c[j] = 0u; start[j] = 0ull;
-            if (t < t_hi) { c[j] = s_off[t]; start[j] = run < cap ? run : cap; run += __ldcg(tile_count + t); }
-        }
-#pragma unroll
-        for (int j = 0; j < kEmitBatch; j++) got[j] = c[j] ? atomicAdd(tile_cursor + t0 + j, c[j]) : 0u;
-#pragma unroll
-        for (int j = 0; j < kEmitBatch; j++)
-            if (c[j]) s_off[t0 + j] = (unsigned)start[j] + got[j];
+    const unsigned *row = run_matrix + (size_t)blockIdx.x * tiles;
+    for (int t = t_lo; t < t_hi; t++) {
+        const unsigned long long start = run < cap ? run : cap;
+        s_off[t] = (unsigned)start + __ldcg(row + t);
+        run += __ldcg(tile_count + t);
     }
     __syncthreads();
-    // pass 2: append
     const unsigned cap32 = (unsigned)cap;
     for (int it = 0; it < gpb_iters; it++) {
         const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + tid);

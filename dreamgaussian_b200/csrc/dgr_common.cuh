@@ -44,20 +44,27 @@ static_assert(sizeof(GeomHeader) == 64, "GeomHeader");
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Gaussians per block of the preprocess / emit kernels = kPreThreads * iters.  Every block keeps a per-tile histogram in
-// shared memory and publishes it with one global atomic per touched tile, so a few thousand Gaussians per block keep that
-// traffic small for big clouds while small clouds still spread over all SMs (about 4 blocks per SM at least).
+// shared memory, reserves its run of every touched tile with one global atomic and leaves the run starts in one row of a
+// [blocks x tiles] matrix: a few thousand Gaussians per block keep that traffic small for big clouds while small clouds
+// still spread over all SMs (about 4 blocks per SM at least).
 __host__ __device__ inline int choose_gpb_iters(int P, int tiles) {
-    (void)tiles;
     long long k = (long long)(P > 0 ? P : 1) / ((long long)kPreThreads * 600);
     if (k < 1) k = 1;
     if (k > 16) k = 16;
+    // ... and the run matrix stays below 64 MB
+    const long long blocks1 = ((long long)(P > 0 ? P : 1) + kPreThreads - 1) / kPreThreads;
+    const long long bytes = blocks1 * (long long)(tiles > 0 ? tiles : 1) * 4;
+    const long long k2 = (bytes + (64ll << 20) - 1) / (64ll << 20);
+    if (k2 > k) k = k2;
+    if (k > 64) k = 64;
     return (int)k;
 }
 
 // geom scratch: [header 256][rec 48 x P][touched u32 x P][backward work counter 256][moments 48 x P (backward)]
+//               [run matrix u32 x blocks x tiles: where block b's instances start inside tile t's range]
 //               (the backward zeroes counter + moments with ONE memset)
 struct GeomLayout {
-    size_t off_rec, off_touched, off_bwdwork, off_gradrec, total;
+    size_t off_rec, off_touched, off_bwdwork, off_gradrec, off_runs, total;
     int tiles, iters, nblocks;
     __host__ __device__ GeomLayout(int P, int H, int W) {
         size_t Pn = P > 0 ? (size_t)P : 1;
@@ -70,15 +77,16 @@ struct GeomLayout {
         off_touched = o; o = align_up(o + Pn * 4, 256);
         off_bwdwork = o; o += 256;
         off_gradrec = o; o = align_up(o + Pn * kGradRecFloats * 4, 256);
+        off_runs = o;    o = align_up(o + (size_t)nblocks * tiles * 4, 256);
         total = o;
     }
 };
 
-// image scratch: [work 256][tile_count u32 x tiles][tile_cursor u32 x tiles][ranges uint2 x tiles][tile_order u32 x tiles]
+// image scratch: [work 256][tile_count u32 x tiles][ranges uint2 x tiles][tile_order u32 x tiles]
 //                [big_list u32 x tiles][n_contrib u32 x HW][final_T f32 x HW]
-// (work, tile_count and tile_cursor are adjacent: the forward zeroes them with ONE memset before the preprocess kernel)
+// (work and tile_count are adjacent: the forward zeroes them with ONE memset before the preprocess kernel)
 struct ImageLayout {
-    size_t off_ranges, off_count, off_cursor, off_order, off_biglist, off_work, off_ncontrib, off_finalT, total;
+    size_t off_ranges, off_count, off_order, off_biglist, off_work, off_ncontrib, off_finalT, total;
     int gx, gy;
     __host__ __device__ ImageLayout(int H, int W) {
         gx = (W + kTile - 1) / kTile; gy = (H + kTile - 1) / kTile;
@@ -87,7 +95,6 @@ struct ImageLayout {
         size_t o = 0;
         off_work = o;     o = align_up(o + 256, 256);
         off_count = o;    o = align_up(o + tiles * 4, 256);
-        off_cursor = o;   o = align_up(o + tiles * 4, 256);
         off_ranges = o;   o = align_up(o + tiles * 8, 256);
         off_order = o;    o = align_up(o + tiles * 4, 256);
         off_biglist = o;  o = align_up(o + tiles * 4, 256);

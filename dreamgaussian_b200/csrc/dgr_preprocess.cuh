@@ -178,9 +178,10 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                       const float *__restrict__ scales, const float *__restrict__ rotations,
                       const float *__restrict__ cov3D_precomp,
                       int *__restrict__ radii, Rec *__restrict__ rec, unsigned *__restrict__ touched_out,
-                      unsigned *__restrict__ tile_count, int tiles, int gpb_iters) {
+                      unsigned *__restrict__ tile_count, unsigned *__restrict__ run_matrix, int tiles, int gpb_iters) {
     // Per-block tile histogram in shared memory (native integer smem atomics); at the end every touched tile's count is
-    // added to the per-tile totals with ONE global atomic per (block, tile) — not one per instance.
+    // added to the per-tile totals with ONE global atomic per (block, tile) — not one per instance — and what the atomic
+    // returns (where this block's run starts inside the tile's range) goes into the block's row of the run matrix.
     extern __shared__ unsigned s_hist[];
     __shared__ FrameConsts fc;
     pdl_trigger();                       // the tile scan may become resident now (it waits for this grid's completion)
@@ -304,9 +305,16 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
     }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < tiles; t += kPreThreads) {
-        const unsigned c = s_hist[t];
-        if (c) atomicAdd(tile_count + t, c);            // result unused -> RED
+    unsigned *row = run_matrix + (size_t)blockIdx.x * tiles;
+    constexpr int kB = 8;                                // atomics in flight per thread
+    for (int t0 = threadIdx.x; t0 < tiles; t0 += kPreThreads * kB) {
+        unsigned c[kB], got[kB];
+#pragma unroll
+        for (int j = 0; j < kB; j++) { const int t = t0 + j * kPreThreads; c[j] = t < tiles ? s_hist[t] : 0u; }
+#pragma unroll
+        for (int j = 0; j < kB; j++) got[j] = c[j] ? atomicAdd(tile_count + t0 + j * kPreThreads, c[j]) : 0u;
+#pragma unroll
+        for (int j = 0; j < kB; j++) { const int t = t0 + j * kPreThreads; if (t < tiles) row[t] = got[j]; }
     }
 }
 

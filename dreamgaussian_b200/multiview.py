@@ -81,9 +81,10 @@ class ViewShardedRasterizer:
                 mc = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
                 self._mc = mc if (mc and os.environ.get("DGR_NO_MULTIMEM") != "1") else 0
                 self._ptrs = (ctypes.c_uint64 * len(self._hdl.buffer_ptrs))(*[int(p) for p in self._hdl.buffer_ptrs])
-                # the flag area follows the gradient data in every rank's copy; in-kernel barriers unless DGR_HOST_BARRIERS=1
+                # the flag area follows the gradient data in every rank's copy.  DGR_INKERNEL_BARRIERS=1: the all-reduce kernel
+                # carries its own two cross-rank barriers (no extra launches); default: symmetric-memory barriers around it
                 self._flags = (ctypes.c_uint64 * len(self._hdl.buffer_ptrs))(*[int(p) + 4 * self.grads.padded for p in self._hdl.buffer_ptrs])
-                self._inkernel = os.environ.get("DGR_HOST_BARRIERS") != "1"
+                self._inkernel = os.environ.get("DGR_INKERNEL_BARRIERS") == "1"
                 self._epoch = 0
                 self._hdl.barrier(channel=0)              # every rank has zeroed its flags before anyone signals
                 self.collective = "own kernel: multimem (NVLS)" if self._mc else "own kernel: p2p two-shot"
@@ -134,6 +135,11 @@ class ViewShardedRasterizer:
                 images.append((color, radii, depth, alpha))
         return images
 
+    def use_nccl(self, why: str):
+        """Drop the library's own all-reduce kernels for this object (e.g. after a failed self-check): plain NCCL from now on."""
+        self._hdl = None
+        self.collective = "nccl all_reduce (%s)" % why
+
     def all_reduce(self):
         """Sum the flat gradient over ranks: this library's NVLink kernel on the symmetric buffer (its two cross-rank
         barriers are inside the kernel), else NCCL (gloo in the CPU tests of the host logic)."""
@@ -155,7 +161,7 @@ class ViewShardedRasterizer:
             if not self._inkernel:
                 self._hdl.barrier(channel=1)
         else:
-            dist.all_reduce(self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
+            dist.all_reduce(self.grads.data if self.grads.data.is_cuda else self.grads.flat, op=dist.ReduceOp.SUM, group=self.pg)
         return self.grads.flat
 
 

@@ -18,7 +18,7 @@ except Exception as e:
 PY
 }
 run default DGR_X=0
-run hostbar DGR_HOST_BARRIERS=1
+run inkernel DGR_INKERNEL_BARRIERS=1
 run p2p DGR_NO_MULTIMEM=1
 run nccl DGR_NO_PEER=1
 timeout 300 python bench.py --steps 300 --warmup 10 --no-rows --no-e2e --no-cpu-baseline > gpurun_out/r2_bench_n1_ref.json 2> gpurun_out/r2_bench_n1_ref.err

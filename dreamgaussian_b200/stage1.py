@@ -355,10 +355,13 @@ class Stage1Trainer:
 
     def _settings(self, elev, azim, radius, res, bg):
         cam = self.scene.orbit_camera(elev, azim, radius, res, res, fovy_deg=self.cfg.fovy)
-        t = lambda a: torch.tensor(np.asarray(a, np.float32), device=self.device)
-        return GaussianRasterizationSettings(image_height=res, image_width=res, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=t(bg),
-                                             scale_modifier=1.0, viewmatrix=t(cam.world_view_transform), projmatrix=t(cam.full_proj_transform),
-                                             sh_degree=self.gaussians.active_sh_degree, campos=t(cam.camera_center), prefiltered=False, debug=False)
+        # one host-to-device copy for the four small camera tensors (the loop is host-bound: every copy is a driver call)
+        buf = np.concatenate([np.append(np.asarray(bg, np.float32).ravel(), 0.0).astype(np.float32), cam.world_view_transform.ravel(), cam.full_proj_transform.ravel(),
+                              cam.camera_center.ravel(), np.zeros(1, np.float32)]).astype(np.float32)
+        t = torch.from_numpy(buf).to(self.device)
+        return GaussianRasterizationSettings(image_height=res, image_width=res, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=t[0:3],
+                                             scale_modifier=1.0, viewmatrix=t[4:20].view(4, 4), projmatrix=t[20:36].view(4, 4),
+                                             sh_degree=self.gaussians.active_sh_degree, campos=t[36:39], prefiltered=False, debug=False)
 
     def render(self, rs, track_stats):
         g = self.gaussians

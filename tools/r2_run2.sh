@@ -13,3 +13,5 @@ timeout 400 python tools/tune.py --tunings "1,2,1;1,2,17;1,2,33;1,2,257;1,2,1025
 timeout 400 python tools/tune.py --opacity init --tunings "1,2,1;1,2,33;1,2,257;1,2,1025;1,1,1;1,1,1025" > gpurun_out/r2_tune_init.log 2>&1; tail -7 gpurun_out/r2_tune_init.log
 bash tools/r2_profile.sh
 bash tools/r2_sanitize.sh
+timeout 900 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; tail -c 2500 gpurun_out/r2_bench_default.json; tail -3 gpurun_out/r2_bench_default.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err; tail -c 600 gpurun_out/r2_bench_reference.json

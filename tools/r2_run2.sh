@@ -7,6 +7,7 @@ rm -f gpurun_out/parity_suite.jsonl
 timeout 240 python -m pytest tests/test_parity_gpu.py -x -q -k "tiny or small_deg3 or odd_size" > gpurun_out/r2_quick.log 2>&1; echo "quick rc=$?" | tee -a gpurun_out/r2_quick.log
 tail -3 gpurun_out/r2_quick.log
 if grep -q "rc=124" gpurun_out/r2_quick.log; then exit 1; fi
+[ -x gpurun_scratch/tma_gather_probe ] && { timeout 120 gpurun_scratch/tma_gather_probe > gpurun_out/r2_tma_probe.log 2>&1; cat gpurun_out/r2_tma_probe.log; }
 timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/r2_suite.log 2>&1; echo "suite rc=$?" | tee -a gpurun_out/r2_suite.log
 tail -12 gpurun_out/r2_suite.log
 timeout 400 python tools/tune.py --tunings "1,2,1;1,2,17;1,2,33;1,2,257;1,2,1025;1,1,1;1,1,1025;2,2,1;1,2,9" > gpurun_out/r2_tune_trained.log 2>&1; tail -10 gpurun_out/r2_tune_trained.log

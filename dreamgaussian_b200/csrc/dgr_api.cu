@@ -196,6 +196,7 @@ __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched
 // thread may change them while another launches (each launch reads every knob once).
 std::atomic<int> g_ppl_fwd{1}, g_ppl_bwd{2}, g_u_fwd{0}, g_u_bwd{0};      // u = 0: the default batching of that sub-tile shape
 std::atomic<bool> g_no_order{false};
+std::atomic<int> g_cta_fwd{0}, g_cta_bwd{0};   // persistent CTAs per SM of the render kernels (0 = as many as fit)
 
 using SmS = SortSmem<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>;
 using SmB = SortSmem<kSortBigThreads, kSortBigCap, kSortBigBuckets>;
@@ -281,6 +282,8 @@ int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order) {
     g_pdl = (tile_order & 8) ? 0 : 1;                   // bit 3: programmatic dependent launches OFF (A/B switch)
     g_u_fwd = (tile_order >> 4) & 7;                    // bits 4-6 / 8-10: hits evaluated together by the forward / backward
     g_u_bwd = (tile_order >> 8) & 7;                    // render kernels (1, 2 or 4; 0 = default of the sub-tile shape)
+    g_cta_fwd = (tile_order >> 12) & 15;                // bits 12-15 / 16-19: persistent CTAs per SM of the forward / backward
+    g_cta_bwd = (tile_order >> 16) & 15;                // render kernels (0 = as many as fit)
     return 0;
 }
 
@@ -357,7 +360,7 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
         DGR_KERNEL("emit_instances", st, s->debug,
                    launch_k(emit_instances_kernel, dim3(nb + 1), dim3(kPreThreads), smem, st, true, g->P, IL.gx, tiles, GL.iters, nb, rec,
                             reinterpret_cast<const unsigned *>(geom + GL.off_touched), (const unsigned *)tile_count, (unsigned long long)capacity,
-                            run_matrix, keys, ranges, hdr, tile_order, work, big_list,
+                            run_matrix, keys, ranges, hdr, tile_order, reinterpret_cast<uint2 *>(image + IL.off_oranges), work, big_list,
                             (volatile unsigned long long *)(ticket ? counts_host : nullptr), (unsigned long long)ticket));
     }
     if (!ticket) {            // copy + event between the kernels (this also ends the chain of programmatic dependent launches here)
@@ -366,9 +369,10 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
         if (count_ready_event) DGR_CUDA(cudaEventRecord((cudaEvent_t)count_ready_event, st));
     }
     if (g->P > 0 && capacity > 0) {
+        const int sort_grid = min(tiles, persistent_grid(dv, tile_sort_gather_kernel, kSortSmallThreads, SmS::bytes));
         DGR_KERNEL("tile_sort_gather", st, s->debug,
-                   launch_k(tile_sort_gather_kernel, dim3(tiles), dim3(kSortSmallThreads), SmS::bytes, st, true, (const unsigned *)tile_order,
-                            (const uint2 *)ranges, keys, rec, ids, recs));
+                   launch_k(tile_sort_gather_kernel, dim3(sort_grid), dim3(kSortSmallThreads), SmS::bytes, st, true, (const TileWork *)work,
+                            reinterpret_cast<const uint2 *>(image + IL.off_oranges), keys, rec, ids, recs));
         if (flags & DGR_FLAG_BIG_TILES)
             DGR_KERNEL("tile_sort_gather_big", st, s->debug,
                        launch_k(tile_sort_gather_big_kernel, dim3(dv->big_grid), dim3(kSortBigThreads), SmB::bytes, st, true, (const TileWork *)work,
@@ -379,7 +383,8 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
 #define DGR_RENDER_FWD(PPL_, U_)                                                                                \
     do {                                                                                                        \
         const int items_ = tiles * SubTile<PPL_>::kPerTile;                                                     \
-        const int grid_ = min(persistent_grid(dv, render_fwd_kernel<PPL_, U_>, kRenderThreads, 0), (items_ + kRenderWarps - 1) / kRenderWarps); \
+        int grid_ = min(persistent_grid(dv, render_fwd_kernel<PPL_, U_>, kRenderThreads, 0), (items_ + kRenderWarps - 1) / kRenderWarps); \
+        if (g_cta_fwd.load() > 0) grid_ = min(grid_, g_cta_fwd.load() * dv->sms);                               \
         DGR_KERNEL("render_fwd", st, s->debug,                                                                  \
                    launch_k(render_fwd_kernel<PPL_, U_>, dim3((unsigned)grid_), dim3(kRenderThreads), 0, st, true, H, W, IL.gx,   \
                             (const unsigned *)tile_order, (unsigned)items_, &work->fwd_next, (const uint2 *)ranges, (const Rec *)recs, \
@@ -422,8 +427,9 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
 #define DGR_RENDER_BWD(PPL_, U_)                                                                                              \
     do {                                                                                                                   \
         const size_t smem_ = sizeof(BwdSmem<PPL_>) * kRenderWarps;                                                         \
-        const int grid_ = min(persistent_grid(dv, render_bwd_kernel<PPL_, U_>, kRenderThreads, smem_),                     \
-                              (tiles * SubTile<PPL_>::kPerTile + kRenderWarps - 1) / kRenderWarps);                        \
+        int grid_ = min(persistent_grid(dv, render_bwd_kernel<PPL_, U_>, kRenderThreads, smem_),                           \
+                        (tiles * SubTile<PPL_>::kPerTile + kRenderWarps - 1) / kRenderWarps);                              \
+        if (g_cta_bwd.load() > 0) grid_ = min(grid_, g_cta_bwd.load() * dv->sms);                                          \
         DGR_KERNEL("render_bwd", st, s->debug,                                                                             \
                    launch_k(render_bwd_kernel<PPL_, U_>, dim3((unsigned)grid_), dim3(kRenderThreads), smem_, st, false, H, W, IL.gx, \
                             reinterpret_cast<const unsigned *>(image + IL.off_order), &work->n_nonempty, bwd_next,         \
@@ -432,8 +438,8 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
                             s->bg, reinterpret_cast<const float *>(image + IL.off_finalT),                                 \
                             reinterpret_cast<const unsigned *>(image + IL.off_ncontrib), gin->dL_dcolor, gin->dL_ddepth, gin->dL_dalpha, grad_rec)); \
     } while (0)
-        if (ppl == 1) { if (ub == 1) DGR_RENDER_BWD(1, 1); else if (ub == 4) DGR_RENDER_BWD(1, 4); else DGR_RENDER_BWD(1, 2); }
-        else { if (ub == 1) DGR_RENDER_BWD(2, 1); else if (ub == 4) DGR_RENDER_BWD(2, 4); else DGR_RENDER_BWD(2, 2); }
+        if (ppl == 1) { if (ub == 2) DGR_RENDER_BWD(1, 2); else if (ub == 4) DGR_RENDER_BWD(1, 4); else DGR_RENDER_BWD(1, 1); }
+        else { if (ub == 2) DGR_RENDER_BWD(2, 2); else if (ub == 4) DGR_RENDER_BWD(2, 4); else DGR_RENDER_BWD(2, 1); }
 #undef DGR_RENDER_BWD
     }
     DGR_KERNEL("preprocess_bwd", st, s->debug, DGR_DISPATCH(launch_pre_bwd, s, g, radii, reinterpret_cast<const unsigned *>(geom + GL.off_touched), grad_rec, gout, st));

@@ -76,7 +76,7 @@ __device__ __forceinline__ void store_sh_grads(float *__restrict__ dL_dshs, int 
 }
 
 template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
-__global__ void __launch_bounds__(kPreThreads, 2)
+__global__ void __launch_bounds__(kPreThreads, 3)
 preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, float scale_modifier,
                       const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
                       const float *__restrict__ campos,

@@ -91,8 +91,9 @@ constexpr int kScanTPT = 8;
 template <int NT>
 __device__ __forceinline__ void
 tile_meta_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long long cap, uint2 *__restrict__ ranges,
-              GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order, TileWork *__restrict__ work,
-              unsigned *__restrict__ big_list, volatile unsigned long long *counts_host, unsigned long long ticket) {
+              GeomHeader *__restrict__ hdr, unsigned *__restrict__ tile_order, uint2 *__restrict__ order_ranges,
+              TileWork *__restrict__ work, unsigned *__restrict__ big_list, volatile unsigned long long *counts_host,
+              unsigned long long ticket) {
     constexpr int NW = NT / 32;
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_carry, s_total;
@@ -176,13 +177,18 @@ tile_meta_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
     for (int t0 = 0; t0 < tiles; t0 += NT) {
         const int t = t0 + tid;
         int bin = -1;
-        if (t < tiles) { const uint2 r = ranges[t]; bin = order_bin(r.y - r.x); }
+        uint2 r = make_uint2(0u, 0u);
+        if (t < tiles) { r = ranges[t]; bin = order_bin(r.y - r.x); }
         const unsigned same = __match_any_sync(0xffffffffu, bin);             // warp-aggregated slot reservation per class
         const int leader = __ffs(same) - 1;
         unsigned base = 0;
         if (bin >= 0 && lane == leader) base = atomicAdd(&s_bin[bin], (unsigned)__popc(same));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (bin >= 0) tile_order[base + __popc(same & ((1u << lane) - 1u))] = (unsigned)t;
+        if (bin >= 0) {
+            const unsigned pos = base + __popc(same & ((1u << lane) - 1u));
+            tile_order[pos] = (unsigned)t;
+            order_ranges[pos] = r;                                            // what the sort kernel reads: no second indirection
+        }
     }
 }
 
@@ -196,34 +202,43 @@ __global__ void __launch_bounds__(kPreThreads)
 emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, int nblocks, const Rec *__restrict__ rec, const unsigned *__restrict__ touched,
                       const unsigned *__restrict__ tile_count, unsigned long long cap, const unsigned *__restrict__ run_matrix,
                       unsigned long long *__restrict__ keys, uint2 *__restrict__ ranges, GeomHeader *__restrict__ hdr,
-                      unsigned *__restrict__ tile_order, TileWork *__restrict__ work, unsigned *__restrict__ big_list,
-                      volatile unsigned long long *counts_host, unsigned long long ticket) {
+                      unsigned *__restrict__ tile_order, uint2 *__restrict__ order_ranges, TileWork *__restrict__ work,
+                      unsigned *__restrict__ big_list, volatile unsigned long long *counts_host, unsigned long long ticket) {
     extern __shared__ unsigned s_off[];
     __shared__ unsigned long long s_part[kPreThreads / 32];
     pdl_trigger();
     pdl_wait();                          // records, touched counts, per-tile totals and run matrix of the preprocess kernel
     if ((int)blockIdx.x == nblocks) {
-        tile_meta_cta<kPreThreads>(tiles, tile_count, cap, ranges, hdr, tile_order, work, big_list, counts_host, ticket);
+        tile_meta_cta<kPreThreads>(tiles, tile_count, cap, ranges, hdr, tile_order, order_ranges, work, big_list, counts_host, ticket);
         return;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // range starts: exclusive scan of the per-tile totals; thread i owns tiles [i K, (i + 1) K)
-    const int K = (tiles + kPreThreads - 1) / kPreThreads;
-    const int t_lo = min(tiles, tid * K), t_hi = min(tiles, t_lo + K);
+    // range starts: exclusive scan of the per-tile totals.  Warp w owns the contiguous tile range [w R, (w + 1) R); its lanes
+    // read 32 consecutive tiles at a time (coalesced, several loads in flight): pass 1 sums the range, pass 2 (after the
+    // warp bases are known) scans it and adds the block's run-matrix row.
+    constexpr int NW = kPreThreads / 32;
+    const int R = ((tiles + NW - 1) / NW + 31) / 32 * 32;
+    const int w_lo = min(tiles, warp * R), w_hi = min(tiles, w_lo + R);
     unsigned long long sum = 0;
-    for (int t = t_lo; t < t_hi; t++) sum += __ldcg(tile_count + t);
-    unsigned long long inc = sum;
+#pragma unroll 4
+    for (int t = w_lo + lane; t < w_hi; t += 32) sum += __ldcg(tile_count + t);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const unsigned long long n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
-    if (lane == 31) s_part[warp] = inc;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_part[warp] = sum;
     __syncthreads();
-    unsigned long long run = inc - sum;
+    unsigned long long run = 0;
     for (int w = 0; w < warp; w++) run += s_part[w];
     const unsigned *row = run_matrix + (size_t)blockIdx.x * tiles;
-    for (int t = t_lo; t < t_hi; t++) {
-        const unsigned long long start = run < cap ? run : cap;
-        s_off[t] = (unsigned)start + __ldcg(row + t);
-        run += __ldcg(tile_count + t);
+    for (int t0 = w_lo; t0 < w_hi; t0 += 32) {
+        const int t = t0 + lane;
+        const unsigned c = t < w_hi ? __ldcg(tile_count + t) : 0u;
+        const unsigned rr = t < w_hi ? __ldcg(row + t) : 0u;
+        unsigned inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+        const unsigned long long start = run + (inc - c);
+        if (t < w_hi) s_off[t] = (unsigned)(start < cap ? start : cap) + rr;
+        run += __shfl_sync(0xffffffffu, inc, 31);
     }
     __syncthreads();
     const unsigned cap32 = (unsigned)cap;
@@ -265,18 +280,21 @@ emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, int nblocks, cons
 // ----------------------------------------------------------------------------------------------------------------
 template <int THREADS, int CAP, int NBK>
 struct SortSmem {
-    static constexpr size_t off_a = 0;                                       // u64 [CAP]  keys as loaded
-    static constexpr size_t off_b = off_a + (size_t)CAP * 8;                 // u64 [CAP]  keys grouped by bucket
+    static constexpr size_t off_b = 0;                                       // u64 [CAP]  keys grouped by bucket
     static constexpr size_t off_start = off_b + (size_t)CAP * 8;             // u32 [NBK + 1] bucket starts
-    static constexpr size_t off_cur = off_start + (NBK + 32) * 4;   // u32 [NBK]     scatter cursors
-    static constexpr size_t off_misc = off_cur + NBK * 4;           // u32 [64]
+    static constexpr size_t off_cur = off_start + (NBK + 32) * 4;            // u32 [NBK]     scatter cursors
+    static constexpr size_t off_misc = off_cur + NBK * 4;                    // u32 [64]
     static constexpr size_t bytes = off_misc + 64 * 4;
 };
 
+// The keys of a tile live in REGISTERS between the phases (CAP / THREADS per thread, one coalesced global read); shared
+// memory holds only the bucket-grouped copy the ranking needs — half the footprint of a two-copy layout, so more tiles are
+// in flight per SM.
 template <int THREADS, int CAP, int NBK>
 __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long long *__restrict__ keys, const Rec *__restrict__ rec,
                                                  unsigned *__restrict__ ids_sorted, Rec *__restrict__ rec_sorted, unsigned char *smem) {
     using SM = SortSmem<THREADS, CAP, NBK>;
+    constexpr int KPT = (CAP + THREADS - 1) / THREADS;
     const int n = (int)(r.y - r.x);
     const int tid = threadIdx.x, lane = tid & 31;
     unsigned long long *gk = keys + r.x;
@@ -293,7 +311,6 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
         __syncthreads();
         return;
     }
-    unsigned long long *A = reinterpret_cast<unsigned long long *>(smem + SM::off_a);
     unsigned long long *B = reinterpret_cast<unsigned long long *>(smem + SM::off_b);
     unsigned *start = reinterpret_cast<unsigned *>(smem + SM::off_start);
     unsigned *cur = reinterpret_cast<unsigned *>(smem + SM::off_cur);
@@ -303,28 +320,31 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
     while (nb < NBK && nb * 2 <= n) nb <<= 1;
     if (tid == 0) { misc[0] = 0xffffffffu; misc[1] = 0u; }
     for (int i = tid; i < nb; i += THREADS) cur[i] = 0u;
-    __syncthreads();
+    unsigned long long k[KPT];
     unsigned lo = 0xffffffffu, hi = 0u;
-    for (int i = tid; i < n; i += THREADS) {
-        const unsigned long long k = gk[i];
-        A[i] = k;
-        const unsigned d = (unsigned)(k >> 32);
-        lo = min(lo, d); hi = max(hi, d);
+#pragma unroll
+    for (int j = 0; j < KPT; j++) {
+        const int i = tid + j * THREADS;
+        k[j] = i < n ? __ldcs(gk + i) : ~0ull;                                // read once, streaming
+        if (i < n) { const unsigned d = (unsigned)(k[j] >> 32); lo = min(lo, d); hi = max(hi, d); }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    __syncthreads();                                   // misc / cur initialised (and the previous tile of this CTA is done with smem)
     if (lane == 0) { atomicMin(&misc[0], lo); atomicMax(&misc[1], hi); }
     __syncthreads();
     const float dmin = __uint_as_float(misc[0]), dmax = __uint_as_float(misc[1]);
     const float scale = (dmax > dmin) ? (float)nb / (dmax - dmin) : 0.f;
     // histogram (cur[] = bucket populations)
-    for (int i = tid; i < n; i += THREADS) {
-        const float d = __uint_as_float((unsigned)(A[i] >> 32));
+#pragma unroll
+    for (int j = 0; j < KPT; j++) {
+        const int i = tid + j * THREADS;
+        const float d = __uint_as_float((unsigned)(k[j] >> 32));
         const int bkt = min(nb - 1, (int)((d - dmin) * scale));               // monotone in d
-        atomicAdd(&cur[bkt], 1u);
+        if (i < n) atomicAdd(&cur[bkt], 1u);
     }
     __syncthreads();
-    // exclusive scan of the nb populations -> start[], cur[] = running cursors.  nb <= 2048 <= 4 per thread at 512 threads.
+    // exclusive scan of the nb populations -> start[], cur[] = running cursors
     {
         constexpr int PER = (NBK + THREADS - 1) / THREADS;
         unsigned v[PER], sum = 0;
@@ -344,23 +364,24 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
     }
     __syncthreads();
     // scatter into buckets (arbitrary order inside a bucket)
-    for (int i = tid; i < n; i += THREADS) {
-        const unsigned long long k = A[i];
-        const float d = __uint_as_float((unsigned)(k >> 32));
+#pragma unroll
+    for (int j = 0; j < KPT; j++) {
+        const int i = tid + j * THREADS;
+        const float d = __uint_as_float((unsigned)(k[j] >> 32));
         const int bkt = min(nb - 1, (int)((d - dmin) * scale));
-        B[atomicAdd(&cur[bkt], 1u)] = k;
+        if (i < n) B[atomicAdd(&cur[bkt], 1u)] = k[j];
     }
     __syncthreads();
     // rank inside the bucket with the full key, write id + record to the final position
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     for (int i = tid; i < n; i += THREADS) {
-        const unsigned long long k = B[i];
-        const float d = __uint_as_float((unsigned)(k >> 32));
-        const int bkt = min(nb - 1, (int)((d - dmin) * scale));
-        const int s = (int)start[bkt], e = (int)start[bkt + 1];
+        const unsigned long long kk = B[i];
+        const float d = __uint_as_float((unsigned)(kk >> 32));
+        const int bk = min(nb - 1, (int)((d - dmin) * scale));
+        const int s = (int)start[bk], e = (int)start[bk + 1];
         int rank = 0;
-        for (int j = s; j < e; j++) rank += (B[j] < k) ? 1 : 0;
-        const unsigned gid = (unsigned)(k & 0xffffffffull);
+        for (int j = s; j < e; j++) rank += (B[j] < kk) ? 1 : 0;
+        const unsigned gid = (unsigned)(kk & 0xffffffffull);
         const size_t pos = (size_t)r.x + s + rank;
         ids_sorted[pos] = gid;
         const Rec *src = rec + gid;
@@ -368,23 +389,31 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
         Rec *dst = rec_sorted + pos;
         stg_f4_hint(&dst->q0, g0, pol_stream); stg_f4_hint(&dst->q1, g1, pol_stream); stg_f4_hint(&dst->q2, g2, pol_stream);
     }
-    __syncthreads();
 }
 
 constexpr int kSortSmallThreads = 512, kSortSmallBuckets = 1024;
-constexpr int kSortBigThreads = 1024, kSortBigCap = 12288, kSortBigBuckets = 2048;     // 192 KB of keys + 16 KB of bucket tables
+constexpr int kSortBigThreads = 1024, kSortBigCap = 12288, kSortBigBuckets = 2048;     // 96 KB of keys + 16 KB of bucket tables
 
-// grid = tiles: one CTA per tile with 0 < n <= kSortSmallCap
-__global__ void __launch_bounds__(kSortSmallThreads)
-tile_sort_gather_kernel(const unsigned *__restrict__ tile_order, const uint2 *__restrict__ ranges, unsigned long long *__restrict__ keys,
+// Persistent grid over the NON-EMPTY tiles in issue order (heaviest first, dealt round-robin to the CTAs): CTA c sorts entries
+// c, c + G, c + 2G ... of the ordered range list the emit kernel's metadata block wrote; the next entry's range is already
+// in flight while a tile is being sorted.  Tiles beyond kSortSmallCap are left to the big-tile kernel.
+__global__ void __launch_bounds__(kSortSmallThreads, 4)
+tile_sort_gather_kernel(const TileWork *__restrict__ work, const uint2 *__restrict__ order_ranges, unsigned long long *__restrict__ keys,
                         const Rec *__restrict__ rec, unsigned *__restrict__ ids_sorted, Rec *__restrict__ rec_sorted) {
     extern __shared__ __align__(16) unsigned char s_sort[];
     pdl_trigger();
     pdl_wait();
-    const uint2 r = ranges[tile_order[blockIdx.x]];
-    const int n = (int)(r.y - r.x);
-    if (n <= 0 || n > kSortSmallCap) return;
-    sort_gather_tile<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>(r, keys, rec, ids_sorted, rec_sorted, s_sort);
+    const unsigned n_tiles = __ldcg(&work->n_nonempty);
+    unsigned i = blockIdx.x;
+    uint2 r = i < n_tiles ? __ldcg(order_ranges + i) : make_uint2(0u, 0u);
+    while (i < n_tiles) {
+        const unsigned inext = i + gridDim.x;
+        const uint2 rnext = inext < n_tiles ? __ldcg(order_ranges + inext) : make_uint2(0u, 0u);
+        const int n = (int)(r.y - r.x);
+        if (n > 0 && n <= kSortSmallCap)
+            sort_gather_tile<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>(r, keys, rec, ids_sorted, rec_sorted, s_sort);
+        i = inext; r = rnext;
+    }
 }
 
 // small persistent grid walking the list of big tiles

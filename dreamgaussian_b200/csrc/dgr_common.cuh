@@ -86,7 +86,7 @@ struct GeomLayout {
 //                [big_list u32 x tiles][n_contrib u32 x HW][final_T f32 x HW]
 // (work and tile_count are adjacent: the forward zeroes them with ONE memset before the preprocess kernel)
 struct ImageLayout {
-    size_t off_ranges, off_count, off_order, off_biglist, off_work, off_ncontrib, off_finalT, total;
+    size_t off_ranges, off_oranges, off_count, off_order, off_biglist, off_work, off_ncontrib, off_finalT, total;
     int gx, gy;
     __host__ __device__ ImageLayout(int H, int W) {
         gx = (W + kTile - 1) / kTile; gy = (H + kTile - 1) / kTile;
@@ -96,6 +96,7 @@ struct ImageLayout {
         off_work = o;     o = align_up(o + 256, 256);
         off_count = o;    o = align_up(o + tiles * 4, 256);
         off_ranges = o;   o = align_up(o + tiles * 8, 256);
+        off_oranges = o;  o = align_up(o + tiles * 8, 256);      // the ranges again, in issue order (sort kernel)
         off_order = o;    o = align_up(o + tiles * 4, 256);
         off_biglist = o;  o = align_up(o + tiles * 4, 256);
         off_ncontrib = o; o = align_up(o + hw * 4, 256);

@@ -169,7 +169,7 @@ __device__ __forceinline__ void project_geo(const FrameConsts &fc, const float3 
 }
 
 template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
-__global__ void __launch_bounds__(kPreThreads, 2)
+__global__ void __launch_bounds__(kPreThreads, 3)
 preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, float scale_modifier,
                       const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
                       const float *__restrict__ campos,

@@ -196,6 +196,7 @@ __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched
 // thread may change them while another launches (each launch reads every knob once).
 std::atomic<int> g_ppl_fwd{1}, g_ppl_bwd{2}, g_u_fwd{0}, g_u_bwd{0};      // u = 0: the default batching of that sub-tile shape
 std::atomic<bool> g_no_order{false};
+std::atomic<int> g_two_ended{1};       // work queue of the render kernels consumed from both ends (dgr_render.cuh)
 std::atomic<int> g_cta_fwd{0}, g_cta_bwd{0};   // persistent CTAs per SM of the render kernels (0 = as many as fit)
 
 using SmS = SortSmem<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>;
@@ -284,6 +285,7 @@ int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order) {
     g_u_bwd = (tile_order >> 8) & 7;                    // render kernels (1, 2 or 4; 0 = default of the sub-tile shape)
     g_cta_fwd = (tile_order >> 12) & 15;                // bits 12-15 / 16-19: persistent CTAs per SM of the forward / backward
     g_cta_bwd = (tile_order >> 16) & 15;                // render kernels (0 = as many as fit)
+    g_two_ended = (tile_order >> 20) & 1 ? 0 : 1;       // bit 20: work queue consumed from the heavy end only (A/B switch)
     return 0;
 }
 
@@ -387,7 +389,8 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
         if (g_cta_fwd.load() > 0) grid_ = min(grid_, g_cta_fwd.load() * dv->sms);                               \
         DGR_KERNEL("render_fwd", st, s->debug,                                                                  \
                    launch_k(render_fwd_kernel<PPL_, U_>, dim3((unsigned)grid_), dim3(kRenderThreads), 0, st, true, H, W, IL.gx,   \
-                            (const unsigned *)tile_order, (unsigned)items_, &work->fwd_next, (const uint2 *)ranges, (const Rec *)recs, \
+                            (const unsigned *)tile_order, reinterpret_cast<const uint2 *>(image + IL.off_oranges),         \
+                            (const unsigned *)&work->n_nonempty, (unsigned)items_, &work->fwd_next, g_two_ended.load(), dv->sms, (const Rec *)recs, \
                             s->bg, out->color, out->depth, out->alpha, n_contrib, final_T));                     \
     } while (0)
     if (ppl == 4) { if (uf == 2) DGR_RENDER_FWD(4, 2); else DGR_RENDER_FWD(4, 1); }
@@ -422,7 +425,7 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
         DevInfo *dv = dev_info();
         if (!dv) return -1;
         const TileWork *work = reinterpret_cast<const TileWork *>(image + IL.off_work);
-        unsigned *bwd_next = reinterpret_cast<unsigned *>(geom + GL.off_bwdwork);
+        unsigned long long *bwd_next = reinterpret_cast<unsigned long long *>(geom + GL.off_bwdwork);
         const int ppl = g_ppl_bwd.load(), ub = g_u_bwd.load();
 #define DGR_RENDER_BWD(PPL_, U_)                                                                                              \
     do {                                                                                                                   \
@@ -432,8 +435,8 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
         if (g_cta_bwd.load() > 0) grid_ = min(grid_, g_cta_bwd.load() * dv->sms);                                          \
         DGR_KERNEL("render_bwd", st, s->debug,                                                                             \
                    launch_k(render_bwd_kernel<PPL_, U_>, dim3((unsigned)grid_), dim3(kRenderThreads), smem_, st, false, H, W, IL.gx, \
-                            reinterpret_cast<const unsigned *>(image + IL.off_order), &work->n_nonempty, bwd_next,         \
-                            reinterpret_cast<const uint2 *>(image + IL.off_ranges),                                        \
+                            reinterpret_cast<const unsigned *>(image + IL.off_order), &work->n_nonempty, bwd_next, g_two_ended.load(), dv->sms, \
+                            reinterpret_cast<const uint2 *>(image + IL.off_oranges),                                       \
                             reinterpret_cast<const Rec *>(binning + BL.off_rec), reinterpret_cast<const unsigned *>(binning + BL.off_ids), \
                             s->bg, reinterpret_cast<const float *>(image + IL.off_finalT),                                 \
                             reinterpret_cast<const unsigned *>(image + IL.off_ncontrib), gin->dL_dcolor, gin->dL_ddepth, gin->dL_dalpha, grad_rec)); \

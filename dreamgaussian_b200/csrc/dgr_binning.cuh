@@ -67,10 +67,9 @@ constexpr int kSortSmallCap = 4096;
 constexpr int kOrderBins = 128;          // log-scale population classes for the heaviest-first issue order
 
 struct TileWork {                        // lives in image scratch
-    unsigned n_big;                      // number of entries of big_list (written by the tile scan)
-    unsigned reserved;
+    unsigned n_big;                      // number of entries of big_list (written by the metadata block)
     unsigned n_nonempty;                 // tiles with at least one instance = the leading entries of tile_order
-    unsigned fwd_next;                   // work counter of the persistent forward render kernel (zeroed by the tile scan)
+    unsigned long long fwd_next;         // work counter of the persistent forward render kernel (zeroed by the metadata block)
 };
 
 __device__ __forceinline__ int order_bin(unsigned count) {
@@ -149,7 +148,7 @@ tile_meta_cta(int tiles, const unsigned *__restrict__ tile_count, unsigned long 
         __syncthreads();
     }
     if (tid == 0) {
-        hdr->n_inst = s_carry; hdr->n_big = s_nbig; work->n_big = s_nbig; work->n_nonempty = s_nne; work->fwd_next = 0u;
+        hdr->n_inst = s_carry; hdr->n_big = s_nbig; work->n_big = s_nbig; work->n_nonempty = s_nne; work->fwd_next = 0ull;
         // The host wants the instance count early (is the caller's capacity guess large enough?).  With a ticket the counts
         // go straight into the caller's pinned, device-mapped host memory: no copy or event between the kernels, the forward
         // chains with programmatic dependent launches while the host polls the ticket.

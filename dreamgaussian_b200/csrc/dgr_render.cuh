@@ -97,10 +97,18 @@ __device__ __forceinline__ int ring_wait(WarpRing &rg, RingState &rs, int seq) {
     return st;
 }
 
-struct RenderWork {                      // lives in image scratch (TileWork) / geom scratch (backward)
-    unsigned next;                       // next work item to hand out
-    unsigned pad[3];
-};
+// Work queue of the persistent render kernels: the (tile, sub-tile) items in issue order (heaviest tile first), ONE 64-bit
+// counter holding how many items have been handed out from the heavy end (low word) and from the light end (high word).
+// Half of the warps of every SM sub-partition take from the heavy end, the other half from the light end, until the two
+// meet: the heavy items are then in flight a few at a time per sub-partition and get re-dealt as warps free up, instead of
+// all starting at once and fixing every sub-partition's load for the whole kernel.  (two_ended = 0: everybody takes from
+// the heavy end.)  An atomicAdd returns both words as they were, so every item is handed out exactly once.
+__device__ __forceinline__ unsigned queue_take(unsigned long long *ctr, bool light, unsigned n) {
+    const unsigned long long old = atomicAdd(ctr, light ? (1ull << 32) : 1ull);
+    const unsigned h = (unsigned)old, l = (unsigned)(old >> 32);
+    if ((unsigned long long)h + l >= n) return 0xffffffffu;
+    return light ? n - 1u - l : h;
+}
 
 // ----------------------------------------------------------------------------------------------------------------
 // Forward.
@@ -110,8 +118,9 @@ struct RenderWork {                      // lives in image scratch (TileWork) / 
 // only the short T / colour update runs in sequence.  Same per-pixel operation order for every U: bit-identical images.
 template <int PPL, int U>
 __global__ void __launch_bounds__(kRenderThreads)
-render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, unsigned n_items,
-                  unsigned *__restrict__ work_next, const uint2 *__restrict__ ranges,
+render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const uint2 *__restrict__ order_ranges,
+                  const unsigned *__restrict__ n_tiles_nonempty, unsigned n_items, unsigned long long *__restrict__ work_next,
+                  int two_ended, int sms,
                   const Rec *__restrict__ rec_sorted, const float *__restrict__ bg, float *__restrict__ out_color,
                   float *__restrict__ out_depth, float *__restrict__ out_alpha, unsigned *__restrict__ n_contrib,
                   float *__restrict__ final_T) {
@@ -126,15 +135,31 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     const size_t HW = (size_t)H * W;
     pdl_wait();                          // sorted records, ranges, order, work counter
 
-    // every tile is visited (heaviest first; the empty ones at the end of the order only write the background)
+    // Work items = (tile, sub-tile) in issue order (heaviest tile first).  The non-empty tiles come first and are handed out
+    // through the atomic counter; the id of the NEXT item is requested while the current one is processed (the round trip of
+    // the atomic is off the critical path).  The empty tiles at the tail of the order only need the background written:
+    // they are dealt statically, no atomics.
+    const unsigned n_queue = __ldcg(n_tiles_nonempty) * (unsigned)ST::kPerTile;
+    const unsigned warp_global = blockIdx.x * kRenderWarps + (threadIdx.x >> 5), warps_total = gridDim.x * kRenderWarps;
+    const bool light = two_ended && (((blockIdx.x / (unsigned)sms) + (threadIdx.x >> 5)) & 1u);
+    unsigned fetched = 0;
+    if (lane == 0) fetched = queue_take(work_next, light, n_queue);
+    bool queue_phase = true;
+    unsigned item = 0, empty_next = n_queue + warp_global;
     for (;;) {
-        unsigned item = 0;
-        if (lane == 0) item = atomicAdd(work_next, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= n_items) break;
-        const int tile = (int)__ldcg(tile_order + item / ST::kPerTile), sub = (int)(item % ST::kPerTile);
+        if (queue_phase) {
+            item = __shfl_sync(0xffffffffu, fetched, 0);
+            if (item >= n_queue) queue_phase = false;
+            else if (lane == 0) fetched = queue_take(work_next, light, n_queue);
+        }
+        if (!queue_phase) {
+            item = empty_next; empty_next += warps_total;
+            if (item >= n_items) break;
+        }
+        const unsigned ot = item / ST::kPerTile;
+        const int tile = (int)__ldcg(tile_order + ot), sub = (int)(item % ST::kPerTile);
+        const uint2 range = __ldcg(order_ranges + ot);
         const int tx = tile % gx, ty = tile / gx;
-        const uint2 range = __ldcg(ranges + tile);
         const int n = (int)(range.y - range.x);
         const int nchunks = (n + kChunk - 1) / kChunk;
         const Rec *src = rec_sorted + range.x;
@@ -260,7 +285,7 @@ struct BwdSmem {
 template <int PPL, int U>
 __global__ void __launch_bounds__(kRenderThreads)
 render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const unsigned *__restrict__ n_tiles_nonempty,
-                  unsigned *__restrict__ work_next, const uint2 *__restrict__ ranges,
+                  unsigned long long *__restrict__ work_next, int two_ended, int sms, const uint2 *__restrict__ order_ranges,
                   const Rec *__restrict__ rec_sorted, const unsigned *__restrict__ ids_sorted, const float *__restrict__ bg,
                   const float *__restrict__ final_T, const unsigned *__restrict__ n_contrib,
                   const float *__restrict__ gC, const float *__restrict__ gD, const float *__restrict__ gA,
@@ -282,14 +307,17 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     const size_t HW = (size_t)H * W;
     const int my_r = lane & (kBatch - 1), my_q = lane / kBatch;      // step 2: parked record, pixel group
 
+    const bool light = two_ended && (((blockIdx.x / (unsigned)sms) + (threadIdx.x >> 5)) & 1u);
+    unsigned fetched = 0;                                            // the next item's id is requested one item ahead
+    if (lane == 0) fetched = queue_take(work_next, light, n_items);
     for (;;) {
-        unsigned item = 0;
-        if (lane == 0) item = atomicAdd(work_next, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
+        const unsigned item = __shfl_sync(0xffffffffu, fetched, 0);
         if (item >= n_items) break;
-        const int tile = (int)__ldcg(tile_order + item / ST::kPerTile), sub = (int)(item % ST::kPerTile);
+        if (lane == 0) fetched = queue_take(work_next, light, n_items);
+        const unsigned ot = item / ST::kPerTile;
+        const int tile = (int)__ldcg(tile_order + ot), sub = (int)(item % ST::kPerTile);
+        const uint2 range = __ldcg(order_ranges + ot);
         const int tx = tile % gx, ty = tile / gx;
-        const uint2 range = __ldcg(ranges + tile);
         const int wx0 = ST::x0(tx, sub), wy0 = ST::y0(ty, sub);
         const int wx1 = wx0 + ST::kW - 1, wy1 = wy0 + ST::kH - 1;
 

@@ -321,11 +321,14 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
     for (int i = tid; i < nb; i += THREADS) cur[i] = 0u;
     unsigned long long k[KPT];
     unsigned lo = 0xffffffffu, hi = 0u;
+    const int kslots = (n + THREADS - 1) / THREADS;                           // slots in use (block-uniform): the loops below stop there
 #pragma unroll
     for (int j = 0; j < KPT; j++) {
-        const int i = tid + j * THREADS;
-        k[j] = i < n ? __ldcs(gk + i) : ~0ull;                                // read once, streaming
-        if (i < n) { const unsigned d = (unsigned)(k[j] >> 32); lo = min(lo, d); hi = max(hi, d); }
+        k[j] = ~0ull;
+        if (j < kslots) {
+            const int i = tid + j * THREADS;
+            if (i < n) { k[j] = __ldcs(gk + i); const unsigned d = (unsigned)(k[j] >> 32); lo = min(lo, d); hi = max(hi, d); }   // read once, streaming
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
@@ -337,10 +340,12 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
     // histogram (cur[] = bucket populations)
 #pragma unroll
     for (int j = 0; j < KPT; j++) {
-        const int i = tid + j * THREADS;
-        const float d = __uint_as_float((unsigned)(k[j] >> 32));
-        const int bkt = min(nb - 1, (int)((d - dmin) * scale));               // monotone in d
-        if (i < n) atomicAdd(&cur[bkt], 1u);
+        if (j < kslots) {
+            const int i = tid + j * THREADS;
+            const float d = __uint_as_float((unsigned)(k[j] >> 32));
+            const int bkt = min(nb - 1, (int)((d - dmin) * scale));           // monotone in d
+            if (i < n) atomicAdd(&cur[bkt], 1u);
+        }
     }
     __syncthreads();
     // exclusive scan of the nb populations -> start[], cur[] = running cursors
@@ -354,9 +359,15 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
         for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
         if (lane == 31) misc[2 + (tid >> 5)] = inc;
         __syncthreads();
-        unsigned off = 0;
-        for (int w = 0; w < (tid >> 5); w++) off += misc[2 + w];
-        unsigned run = off + inc - sum;
+        if (tid < 32) {                                // exclusive scan of the (at most 32) warp totals
+            const unsigned w = tid < THREADS / 32 ? misc[2 + tid] : 0u;
+            unsigned wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            misc[2 + tid] = wi - w;
+        }
+        __syncthreads();
+        unsigned run = misc[2 + (tid >> 5)] + inc - sum;
 #pragma unroll
         for (int j = 0; j < PER; j++) { const int b = tid * PER + j; if (b < nb) { start[b] = run; cur[b] = run; } run += v[j]; }
         if (tid == 0) start[nb] = (unsigned)n;
@@ -365,10 +376,12 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
     // scatter into buckets (arbitrary order inside a bucket)
 #pragma unroll
     for (int j = 0; j < KPT; j++) {
-        const int i = tid + j * THREADS;
-        const float d = __uint_as_float((unsigned)(k[j] >> 32));
-        const int bkt = min(nb - 1, (int)((d - dmin) * scale));
-        if (i < n) B[atomicAdd(&cur[bkt], 1u)] = k[j];
+        if (j < kslots) {
+            const int i = tid + j * THREADS;
+            const float d = __uint_as_float((unsigned)(k[j] >> 32));
+            const int bkt = min(nb - 1, (int)((d - dmin) * scale));
+            if (i < n) B[atomicAdd(&cur[bkt], 1u)] = k[j];
+        }
     }
     __syncthreads();
     // rank inside the bucket with the full key, write id + record to the final position

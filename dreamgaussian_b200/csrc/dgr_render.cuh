@@ -136,21 +136,21 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     pdl_wait();                          // sorted records, ranges, order, work counter
 
     // Work items = (tile, sub-tile) in issue order (heaviest tile first).  The non-empty tiles come first and are handed out
-    // through the atomic counter; the id of the NEXT item is requested while the current one is processed (the round trip of
-    // the atomic is off the critical path).  The empty tiles at the tail of the order only need the background written:
-    // they are dealt statically, no atomics.
+    // through the atomic counter.  The empty tiles at the tail of the order only need the background written: they are dealt
+    // statically, no atomics.
     const unsigned n_queue = __ldcg(n_tiles_nonempty) * (unsigned)ST::kPerTile;
     const unsigned warp_global = blockIdx.x * kRenderWarps + (threadIdx.x >> 5), warps_total = gridDim.x * kRenderWarps;
     const bool light = two_ended && (((blockIdx.x / (unsigned)sms) + (threadIdx.x >> 5)) & 1u);
-    unsigned fetched = 0;
-    if (lane == 0) fetched = queue_take(work_next, light, n_queue);
     bool queue_phase = true;
     unsigned item = 0, empty_next = n_queue + warp_global;
     for (;;) {
         if (queue_phase) {
+            // (the item is taken when the warp is ready for it, not earlier: reserving the next item ahead of time would
+            //  hand out the whole queue at the start and leave nothing to balance with — measured 58 -> 72 us)
+            unsigned fetched = 0;
+            if (lane == 0) fetched = queue_take(work_next, light, n_queue);
             item = __shfl_sync(0xffffffffu, fetched, 0);
             if (item >= n_queue) queue_phase = false;
-            else if (lane == 0) fetched = queue_take(work_next, light, n_queue);
         }
         if (!queue_phase) {
             item = empty_next; empty_next += warps_total;
@@ -308,12 +308,11 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     const int my_r = lane & (kBatch - 1), my_q = lane / kBatch;      // step 2: parked record, pixel group
 
     const bool light = two_ended && (((blockIdx.x / (unsigned)sms) + (threadIdx.x >> 5)) & 1u);
-    unsigned fetched = 0;                                            // the next item's id is requested one item ahead
-    if (lane == 0) fetched = queue_take(work_next, light, n_items);
     for (;;) {
+        unsigned fetched = 0;                                        // taken when the warp is ready for it (see the forward)
+        if (lane == 0) fetched = queue_take(work_next, light, n_items);
         const unsigned item = __shfl_sync(0xffffffffu, fetched, 0);
         if (item >= n_items) break;
-        if (lane == 0) fetched = queue_take(work_next, light, n_items);
         const unsigned ot = item / ST::kPerTile;
         const int tile = (int)__ldcg(tile_order + ot), sub = (int)(item % ST::kPerTile);
         const uint2 range = __ldcg(order_ranges + ot);

@@ -5,6 +5,7 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -196,7 +197,8 @@ __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched
 // thread may change them while another launches (each launch reads every knob once).
 std::atomic<int> g_ppl_fwd{1}, g_ppl_bwd{2}, g_u_fwd{0}, g_u_bwd{0};      // u = 0: the default batching of that sub-tile shape
 std::atomic<bool> g_no_order{false};
-std::atomic<int> g_two_ended{1};       // work queue of the render kernels consumed from both ends (dgr_render.cuh)
+std::atomic<int> g_two_ended{0};
+std::atomic<int> g_cost_order{1};      // backward work ordered by the cost the forward measured (dgr_render.cuh)       // work queue of the render kernels consumed from both ends (dgr_render.cuh)
 std::atomic<int> g_cta_fwd{0}, g_cta_bwd{0};   // persistent CTAs per SM of the render kernels (0 = as many as fit)
 
 using SmS = SortSmem<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>;
@@ -285,7 +287,8 @@ int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order) {
     g_u_bwd = (tile_order >> 8) & 7;                    // render kernels (1, 2 or 4; 0 = default of the sub-tile shape)
     g_cta_fwd = (tile_order >> 12) & 15;                // bits 12-15 / 16-19: persistent CTAs per SM of the forward / backward
     g_cta_bwd = (tile_order >> 16) & 15;                // render kernels (0 = as many as fit)
-    g_two_ended = (tile_order >> 20) & 1 ? 0 : 1;       // bit 20: work queue consumed from the heavy end only (A/B switch)
+    g_two_ended = (tile_order >> 20) & 1;               // bit 20: work queue consumed from both ends (experiment; measured slower)
+    g_cost_order = (tile_order >> 21) & 1 ? 0 : 1;      // bit 21: backward work in tile-population order instead of measured cost
     return 0;
 }
 
@@ -311,8 +314,8 @@ int dgr_forward_preprocess(const DgrSettings *s, const DgrGaussians *g, void *ge
     GeomLayout L(g->P, s->image_height, s->image_width);
     ImageLayout IL(s->image_height, s->image_width);
     if ((size_t)L.tiles * 4 > kMaxTileSmem) return fail(-3, "image has more than 51200 tiles (16x16): not supported");
-    // one memset: the work block + the per-tile instance totals the preprocess kernel adds into
-    DGR_CUDA(cudaMemsetAsync(image + IL.off_work, 0, (IL.off_count - IL.off_work) + (size_t)L.tiles * 4, st));
+    // one memset: the work block + the per-tile instance totals the preprocess kernel adds into + the backward cost accumulators
+    DGR_CUDA(cudaMemsetAsync(image + IL.off_work, 0, (IL.off_cost - IL.off_work) + (size_t)L.tiles * 8 * 4, st));
     if (g->P > 0) {
         if (!radii) return fail(-1, "radii is NULL");
         DGR_KERNEL("preprocess_fwd", st, s->debug, DGR_DISPATCH(launch_pre_fwd, s, g, radii, geom, L, reinterpret_cast<unsigned *>(image + IL.off_count), st));
@@ -354,13 +357,18 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
     DevInfo *dv = dev_info();
     if (!dv) return -1;
     (void)(flags & DGR_FLAG_RERUN);           // a re-run only repeats the scan from the (still valid) per-tile totals
-    // (a re-run with corrected guesses repeats everything from here: per-tile totals and run matrix are still valid)
+    // (a re-run with corrected guesses repeats everything from here: per-tile totals and run matrix are still valid; what the
+    //  first, clipped render pass filed as backward costs is not)
+    if (flags & DGR_FLAG_RERUN) {
+        DGR_CUDA(cudaMemsetAsync(image + IL.off_cost, 0, (size_t)tiles * 8 * 4, st));
+        DGR_CUDA(cudaMemsetAsync(reinterpret_cast<char *>(work) + offsetof(TileWork, cost_bpt), 0, sizeof(TileWork) - offsetof(TileWork, cost_bpt), st));
+    }
     {
         // instance emission; its extra block publishes ranges / order / counts (capacity 0: only that block has work to do)
         const size_t smem = (size_t)tiles * 4;
         const int nb = (g->P > 0 && capacity > 0) ? GL.nblocks : 0;
         DGR_KERNEL("emit_instances", st, s->debug,
-                   launch_k(emit_instances_kernel, dim3(nb + 1), dim3(kPreThreads), smem, st, true, g->P, IL.gx, tiles, GL.iters, nb, rec,
+                   launch_k(emit_instances_kernel, dim3(nb + 1), dim3(kPreThreads), smem, st, !(flags & DGR_FLAG_RERUN), g->P, IL.gx, tiles, GL.iters, nb, rec,
                             reinterpret_cast<const unsigned *>(geom + GL.off_touched), (const unsigned *)tile_count, (unsigned long long)capacity,
                             run_matrix, keys, ranges, hdr, tile_order, reinterpret_cast<uint2 *>(image + IL.off_oranges), work, big_list,
                             (volatile unsigned long long *)(ticket ? counts_host : nullptr), (unsigned long long)ticket));
@@ -382,6 +390,12 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
     }
     // persistent forward render: every (tile, sub-tile) is a work item, handed out heaviest tile first
     const int ppl = g_ppl_fwd.load(), uf = g_u_fwd.load();
+    CostOrder co{};
+    if (g_cost_order.load()) {
+        co.cost_acc = reinterpret_cast<unsigned *>(image + IL.off_cost); co.cls_count = work->cls_count;
+        co.cls_items = reinterpret_cast<unsigned *>(image + IL.off_clsitems); co.cost_bpt = &work->cost_bpt;
+        co.tiles = tiles; co.bwd_ppl = g_ppl_bwd.load();
+    }
 #define DGR_RENDER_FWD(PPL_, U_)                                                                                \
     do {                                                                                                        \
         const int items_ = tiles * SubTile<PPL_>::kPerTile;                                                     \
@@ -390,7 +404,7 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
         DGR_KERNEL("render_fwd", st, s->debug,                                                                  \
                    launch_k(render_fwd_kernel<PPL_, U_>, dim3((unsigned)grid_), dim3(kRenderThreads), 0, st, true, H, W, IL.gx,   \
                             (const unsigned *)tile_order, reinterpret_cast<const uint2 *>(image + IL.off_oranges),         \
-                            (const unsigned *)&work->n_nonempty, (unsigned)items_, &work->fwd_next, g_two_ended.load(), dv->sms, (const Rec *)recs, \
+                            (const unsigned *)&work->n_nonempty, (unsigned)items_, &work->fwd_next, g_two_ended.load(), dv->sms, co, (const Rec *)recs, \
                             s->bg, out->color, out->depth, out->alpha, n_contrib, final_T));                     \
     } while (0)
     if (ppl == 4) { if (uf == 2) DGR_RENDER_FWD(4, 2); else DGR_RENDER_FWD(4, 1); }
@@ -427,6 +441,13 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
         const TileWork *work = reinterpret_cast<const TileWork *>(image + IL.off_work);
         unsigned long long *bwd_next = reinterpret_cast<unsigned long long *>(geom + GL.off_bwdwork);
         const int ppl = g_ppl_bwd.load(), ub = g_u_bwd.load();
+        CostOrder co{};
+        if (g_cost_order.load()) {            // (read-only here; the kernel checks that the forward grouped its costs for this shape)
+            TileWork *wk = const_cast<TileWork *>(work);
+            co.cost_acc = const_cast<unsigned *>(reinterpret_cast<const unsigned *>(image + IL.off_cost)); co.cls_count = wk->cls_count;
+            co.cls_items = const_cast<unsigned *>(reinterpret_cast<const unsigned *>(image + IL.off_clsitems)); co.cost_bpt = &wk->cost_bpt;
+            co.tiles = tiles; co.bwd_ppl = ppl == 1 ? 1 : 2;
+        }
 #define DGR_RENDER_BWD(PPL_, U_)                                                                                              \
     do {                                                                                                                   \
         const size_t smem_ = sizeof(BwdSmem<PPL_>) * kRenderWarps;                                                         \
@@ -435,7 +456,7 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
         if (g_cta_bwd.load() > 0) grid_ = min(grid_, g_cta_bwd.load() * dv->sms);                                          \
         DGR_KERNEL("render_bwd", st, s->debug,                                                                             \
                    launch_k(render_bwd_kernel<PPL_, U_>, dim3((unsigned)grid_), dim3(kRenderThreads), smem_, st, false, H, W, IL.gx, \
-                            reinterpret_cast<const unsigned *>(image + IL.off_order), &work->n_nonempty, bwd_next, g_two_ended.load(), dv->sms, \
+                            reinterpret_cast<const unsigned *>(image + IL.off_order), &work->n_nonempty, bwd_next, g_two_ended.load(), dv->sms, co, \
                             reinterpret_cast<const uint2 *>(image + IL.off_oranges),                                       \
                             reinterpret_cast<const Rec *>(binning + BL.off_rec), reinterpret_cast<const unsigned *>(binning + BL.off_ids), \
                             s->bg, reinterpret_cast<const float *>(image + IL.off_finalT),                                 \

@@ -66,11 +66,15 @@ __device__ __forceinline__ void bitonic_sort_cta(unsigned long long *a, int n) {
 constexpr int kSortSmallCap = 4096;
 constexpr int kOrderBins = 128;          // log-scale population classes for the heaviest-first issue order
 
-struct TileWork {                        // lives in image scratch
+struct TileWork {                        // lives in image scratch (256 bytes, zeroed by the forward's memset)
     unsigned n_big;                      // number of entries of big_list (written by the metadata block)
     unsigned n_nonempty;                 // tiles with at least one instance = the leading entries of tile_order
     unsigned long long fwd_next;         // work counter of the persistent forward render kernel (zeroed by the metadata block)
+    unsigned cost_bpt;                   // backward items per tile the forward grouped its measured costs for (0: none)
+    unsigned pad[3];
+    unsigned cls_count[kCostClasses];    // backward work items per measured-cost class (filled by the forward render kernel)
 };
+static_assert(sizeof(TileWork) <= 256, "TileWork");
 
 __device__ __forceinline__ int order_bin(unsigned count) {
     // descending population class: 0 = heaviest.  class = 4 * floor(log2(count)) + next two mantissa bits

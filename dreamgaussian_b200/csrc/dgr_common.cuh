@@ -82,11 +82,14 @@ struct GeomLayout {
     }
 };
 
+constexpr int kCostClasses = 32;         // log-scale classes of the measured forward cost of a backward work item
+
 // image scratch: [work 256][tile_count u32 x tiles][ranges uint2 x tiles][tile_order u32 x tiles]
 //                [big_list u32 x tiles][n_contrib u32 x HW][final_T f32 x HW]
-// (work and tile_count are adjacent: the forward zeroes them with ONE memset before the preprocess kernel)
+//                ... [cost accumulators u32 x 8 tiles] ... [cost-class item lists u32 x 32 x 8 tiles]
+// (work, tile_count and the cost accumulators are adjacent: the forward zeroes them with ONE memset before the preprocess kernel)
 struct ImageLayout {
-    size_t off_ranges, off_oranges, off_count, off_order, off_biglist, off_work, off_ncontrib, off_finalT, total;
+    size_t off_ranges, off_oranges, off_count, off_cost, off_order, off_biglist, off_work, off_ncontrib, off_finalT, off_clsitems, total;
     int gx, gy;
     __host__ __device__ ImageLayout(int H, int W) {
         gx = (W + kTile - 1) / kTile; gy = (H + kTile - 1) / kTile;
@@ -95,12 +98,14 @@ struct ImageLayout {
         size_t o = 0;
         off_work = o;     o = align_up(o + 256, 256);
         off_count = o;    o = align_up(o + tiles * 4, 256);
+        off_cost = o;     o = align_up(o + tiles * 8 * 4, 256);    // measured cost of every backward work item (zeroed with the totals)
         off_ranges = o;   o = align_up(o + tiles * 8, 256);
         off_oranges = o;  o = align_up(o + tiles * 8, 256);      // the ranges again, in issue order (sort kernel)
         off_order = o;    o = align_up(o + tiles * 4, 256);
         off_biglist = o;  o = align_up(o + tiles * 4, 256);
         off_ncontrib = o; o = align_up(o + hw * 4, 256);
         off_finalT = o;   o = align_up(o + hw * 4, 256);
+        off_clsitems = o; o = align_up(o + (size_t)kCostClasses * tiles * 8 * 4, 256);   // backward work items grouped by measured cost class
         total = o;
     }
 };

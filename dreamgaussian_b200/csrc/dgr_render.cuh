@@ -110,6 +110,27 @@ __device__ __forceinline__ unsigned queue_take(unsigned long long *ctr, bool lig
     return light ? n - 1u - l : h;
 }
 
+// Measured-cost ordering of the backward.  How long a sub-tile's list really is (early termination!) is only known after
+// the forward has walked it, and the tile population the forward orders its own work by is a poor predictor of it.  So the
+// forward records what every backward work item cost it (records tested + records that hit; two forward items feed one
+// backward item when the backward uses larger sub-tiles) and appends the item to the list of its log-scale cost class; the
+// backward hands the items out class by class, heaviest first — a longest-processing-time-first order by MEASURED cost,
+// which deals the heavy items evenly over the SMs and leaves only light ones for the tail.
+__device__ __forceinline__ int cost_class(unsigned c) {             // 0 = lightest ... kCostClasses-1 = heaviest
+    const int lg = 31 - __clz(c | 1u);
+    const int half = lg >= 1 ? (int)((c >> (lg - 1)) & 1u) : 0;
+    return min(kCostClasses - 1, 2 * lg + half);
+}
+
+struct CostOrder {                       // image scratch pieces (all may be NULL: no measured-cost ordering)
+    unsigned *cost_acc;                  // [tiles * 8]  sum of (cost << 2 | 1) of the forward items of a backward item
+    unsigned *cls_count;                 // [kCostClasses]
+    unsigned *cls_items;                 // [kCostClasses][tiles * 8]  ordered-tile index * 8 + backward sub-tile
+    unsigned *cost_bpt;                  // TileWork::cost_bpt
+    int tiles;
+    int bwd_ppl;                         // sub-tile shape the backward will use (1 or 2)
+};
+
 // ----------------------------------------------------------------------------------------------------------------
 // Forward.
 // ----------------------------------------------------------------------------------------------------------------
@@ -120,7 +141,7 @@ template <int PPL, int U>
 __global__ void __launch_bounds__(kRenderThreads)
 render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const uint2 *__restrict__ order_ranges,
                   const unsigned *__restrict__ n_tiles_nonempty, unsigned n_items, unsigned long long *__restrict__ work_next,
-                  int two_ended, int sms,
+                  int two_ended, int sms, CostOrder co,
                   const Rec *__restrict__ rec_sorted, const float *__restrict__ bg, float *__restrict__ out_color,
                   float *__restrict__ out_depth, float *__restrict__ out_alpha, unsigned *__restrict__ n_contrib,
                   float *__restrict__ final_T) {
@@ -140,6 +161,8 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     // statically, no atomics.
     const unsigned n_queue = __ldcg(n_tiles_nonempty) * (unsigned)ST::kPerTile;
     const unsigned warp_global = blockIdx.x * kRenderWarps + (threadIdx.x >> 5), warps_total = gridDim.x * kRenderWarps;
+    const bool costing = co.cost_acc != nullptr && PPL <= co.bwd_ppl;                 // forward sub-tiles nest in the backward's
+    if (costing && blockIdx.x == 0 && threadIdx.x == 0) *co.cost_bpt = (unsigned)(8 / co.bwd_ppl);
     const bool light = two_ended && (((blockIdx.x / (unsigned)sms) + (threadIdx.x >> 5)) & 1u);
     bool queue_phase = true;
     unsigned item = 0, empty_next = n_queue + warp_global;
@@ -184,6 +207,7 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
             all_done = all_done && done[p];
         }
         bool warp_done = __all_sync(0xffffffffu, all_done);
+        unsigned cost = 0;
         for (int c = 0; c < nchunks && !warp_done; c++) {
             const int s = ring_wait(rg, rs, c);
             rs.waited = c + 1;
@@ -191,6 +215,7 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
             bool hit = false;
             if (lane < cnt) hit = record_hits_subtile(rg.rec[s][lane], wx0, wx1, wy0, wy1);
             unsigned mask = __ballot_sync(0xffffffffu, hit);
+            cost += 2u + 4u * (unsigned)__popc(mask);
             while (mask) {
                 int js[U];
                 int nh = 0;
@@ -262,6 +287,29 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
                 final_T[pix] = T[p];
             }
         }
+        if (costing && n > 0) {
+            // this forward item's share of its backward item's cost; whoever completes the backward item files it under its class
+            bool contrib = false;
+#pragma unroll
+            for (int p = 0; p < PPL; p++) contrib = contrib || (last[p] > 0u);
+            contrib = __any_sync(0xffffffffu, contrib);
+            if (lane == 0) {
+                const int bpt = 8 / co.bwd_ppl, parts = co.bwd_ppl / PPL;                 // forward items per backward item
+                const int bsub = co.bwd_ppl == 1 ? ((wy0 & 15) >> 2) * 2 + ((wx0 & 15) >> 3)
+                                                 : ((wy0 & 15) >> 3) * 2 + ((wx0 & 15) >> 3);
+                const unsigned mine = contrib ? cost + 1u : 0u;
+                const unsigned old = atomicAdd(co.cost_acc + (size_t)tile * 8 + bsub, (mine << 2) | 1u);
+                if ((int)(old & 3u) + 1 == parts) {
+                    const unsigned total = (old >> 2) + mine;
+                    if (total > 0u) {
+                        const int cls = cost_class(total);
+                        const unsigned pos = atomicAdd(co.cls_count + cls, 1u);
+                        co.cls_items[(size_t)cls * co.tiles * 8 + pos] = ot * 8u + (unsigned)bsub;
+                    }
+                }
+                (void)bpt;
+            }
+        }
         __syncwarp();
     }
 }
@@ -285,7 +333,7 @@ struct BwdSmem {
 template <int PPL, int U>
 __global__ void __launch_bounds__(kRenderThreads)
 render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const unsigned *__restrict__ n_tiles_nonempty,
-                  unsigned long long *__restrict__ work_next, int two_ended, int sms, const uint2 *__restrict__ order_ranges,
+                  unsigned long long *__restrict__ work_next, int two_ended, int sms, CostOrder co, const uint2 *__restrict__ order_ranges,
                   const Rec *__restrict__ rec_sorted, const unsigned *__restrict__ ids_sorted, const float *__restrict__ bg,
                   const float *__restrict__ final_T, const unsigned *__restrict__ n_contrib,
                   const float *__restrict__ gC, const float *__restrict__ gD, const float *__restrict__ gA,
@@ -302,7 +350,16 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     RingState rs;
     pdl_trigger();                       // the per-Gaussian backward may take the SM resources this grid's tail frees
     ring_init(rg, rs, lane);
-    const unsigned n_items = __ldcg(n_tiles_nonempty) * (unsigned)ST::kPerTile;
+    // work list: the measured-cost classes of the forward (heaviest class first) when it grouped its costs for this sub-tile
+    // shape, else every sub-tile of the non-empty tiles in population order
+    const bool by_cost = co.cost_acc != nullptr && __ldcg(co.cost_bpt) == (unsigned)ST::kPerTile;
+    unsigned cum_end = 0;                                            // lane L: items in classes kCostClasses-1 .. kCostClasses-1-L
+    if (by_cost) {
+        cum_end = __ldcg(co.cls_count + (kCostClasses - 1 - lane));
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, cum_end, o); if (lane >= o) cum_end += t; }
+    }
+    const unsigned n_items = by_cost ? __shfl_sync(0xffffffffu, cum_end, 31) : __ldcg(n_tiles_nonempty) * (unsigned)ST::kPerTile;
     const float b0 = __ldg(bg), b1 = __ldg(bg + 1), b2 = __ldg(bg + 2);
     const size_t HW = (size_t)H * W;
     const int my_r = lane & (kBatch - 1), my_q = lane / kBatch;      // step 2: parked record, pixel group
@@ -311,10 +368,16 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     for (;;) {
         unsigned fetched = 0;                                        // taken when the warp is ready for it (see the forward)
         if (lane == 0) fetched = queue_take(work_next, light, n_items);
-        const unsigned item = __shfl_sync(0xffffffffu, fetched, 0);
+        unsigned item = __shfl_sync(0xffffffffu, fetched, 0);
         if (item >= n_items) break;
-        const unsigned ot = item / ST::kPerTile;
-        const int tile = (int)__ldcg(tile_order + ot), sub = (int)(item % ST::kPerTile);
+        if (by_cost) {                                               // rank in the heaviest-first order -> (class, position) -> item
+            const unsigned before = __ballot_sync(0xffffffffu, cum_end <= item);
+            const int k = __popc(before);                            // classes completely in front of this rank
+            const unsigned base = k ? __shfl_sync(0xffffffffu, cum_end, k - 1) : 0u;
+            item = __ldcg(co.cls_items + (size_t)(kCostClasses - 1 - k) * co.tiles * 8 + (item - base));
+        }
+        const unsigned ot = by_cost ? item / 8u : item / ST::kPerTile;
+        const int tile = (int)__ldcg(tile_order + ot), sub = (int)(by_cost ? item % 8u : item % ST::kPerTile);
         const uint2 range = __ldcg(order_ranges + ot);
         const int tx = tile % gx, ty = tile / gx;
         const int wx0 = ST::x0(tx, sub), wy0 = ST::y0(ty, sub);

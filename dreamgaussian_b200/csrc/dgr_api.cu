@@ -195,7 +195,7 @@ __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched
 
 // tuning knobs (dgr_set_tuning): pixels per lane of the render kernels, heaviest-first tile order on/off.  Atomics: any host
 // thread may change them while another launches (each launch reads every knob once).
-std::atomic<int> g_ppl_fwd{1}, g_ppl_bwd{2}, g_u_fwd{0}, g_u_bwd{0};      // u = 0: the default batching of that sub-tile shape
+std::atomic<int> g_ppl_fwd{1}, g_ppl_bwd{1}, g_u_fwd{0}, g_u_bwd{0};      // u = 0: the default batching of that sub-tile shape
 std::atomic<bool> g_no_order{false};
 std::atomic<int> g_two_ended{0};
 std::atomic<int> g_cost_order{1};      // backward work ordered by the cost the forward measured (dgr_render.cuh)       // work queue of the render kernels consumed from both ends (dgr_render.cuh)

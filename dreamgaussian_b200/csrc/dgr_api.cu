@@ -198,7 +198,8 @@ __global__ void debug_geom_kernel(int P, const Rec *rec, const unsigned *touched
 std::atomic<int> g_ppl_fwd{1}, g_ppl_bwd{1}, g_u_fwd{0}, g_u_bwd{0};      // u = 0: the default batching of that sub-tile shape
 std::atomic<bool> g_no_order{false};
 std::atomic<int> g_two_ended{0};
-std::atomic<int> g_cost_order{1};      // backward work ordered by the cost the forward measured (dgr_render.cuh)       // work queue of the render kernels consumed from both ends (dgr_render.cuh)
+std::atomic<int> g_cost_order{1};
+std::atomic<int> g_lazy{0};            // record staging of the render kernels: 0 = by id when the caller expects big tiles, 1 = always sorted copy, 2 = always by id      // backward work ordered by the cost the forward measured (dgr_render.cuh)       // work queue of the render kernels consumed from both ends (dgr_render.cuh)
 std::atomic<int> g_cta_fwd{0}, g_cta_bwd{0};   // persistent CTAs per SM of the render kernels (0 = as many as fit)
 
 using SmS = SortSmem<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>;
@@ -289,6 +290,7 @@ int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order) {
     g_cta_bwd = (tile_order >> 16) & 15;                // render kernels (0 = as many as fit)
     g_two_ended = (tile_order >> 20) & 1;               // bit 20: work queue consumed from both ends (experiment; measured slower)
     g_cost_order = (tile_order >> 21) & 1 ? 0 : 1;      // bit 21: backward work in tile-population order instead of measured cost
+    g_lazy = (tile_order >> 22) & 3;                    // bits 22-23: record staging 0 = auto, 1 = always the sorted copy, 2 = always by id
     return 0;
 }
 
@@ -378,15 +380,17 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
             DGR_CUDA(cudaMemcpyAsync(counts_host, geom, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         if (count_ready_event) DGR_CUDA(cudaEventRecord((cudaEvent_t)count_ready_event, st));
     }
+    const int lz = g_lazy.load();
+    const bool lazy = lz == 2 || (lz == 0 && (flags & DGR_FLAG_BIG_TILES));
     if (g->P > 0 && capacity > 0) {
         const int sort_grid = min(tiles, persistent_grid(dv, tile_sort_gather_kernel, kSortSmallThreads, SmS::bytes));
         DGR_KERNEL("tile_sort_gather", st, s->debug,
                    launch_k(tile_sort_gather_kernel, dim3(sort_grid), dim3(kSortSmallThreads), SmS::bytes, st, true, (const TileWork *)work,
-                            reinterpret_cast<const uint2 *>(image + IL.off_oranges), keys, rec, ids, recs));
+                            reinterpret_cast<const uint2 *>(image + IL.off_oranges), keys, rec, ids, recs, lazy ? 0 : 1));
         if (flags & DGR_FLAG_BIG_TILES)
             DGR_KERNEL("tile_sort_gather_big", st, s->debug,
                        launch_k(tile_sort_gather_big_kernel, dim3(dv->big_grid), dim3(kSortBigThreads), SmB::bytes, st, true, (const TileWork *)work,
-                                (const unsigned *)big_list, (const uint2 *)ranges, keys, rec, ids, recs));
+                                (const unsigned *)big_list, (const uint2 *)ranges, keys, rec, ids, recs, lazy ? 0 : 1));
     }
     // persistent forward render: every (tile, sub-tile) is a work item, handed out heaviest tile first
     const int ppl = g_ppl_fwd.load(), uf = g_u_fwd.load();
@@ -404,7 +408,8 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
         DGR_KERNEL("render_fwd", st, s->debug,                                                                  \
                    launch_k(render_fwd_kernel<PPL_, U_>, dim3((unsigned)grid_), dim3(kRenderThreads), 0, st, true, H, W, IL.gx,   \
                             (const unsigned *)tile_order, reinterpret_cast<const uint2 *>(image + IL.off_oranges),         \
-                            (const unsigned *)&work->n_nonempty, (unsigned)items_, &work->fwd_next, g_two_ended.load(), dv->sms, co, (const Rec *)recs, \
+                            (const unsigned *)&work->n_nonempty, (unsigned)items_, &work->fwd_next, g_two_ended.load(), dv->sms, co, lazy ? 1 : 0, \
+                            &work->lazy, (const Rec *)recs, rec, (const unsigned *)ids,                                      \
                             s->bg, out->color, out->depth, out->alpha, n_contrib, final_T));                     \
     } while (0)
     if (ppl == 4) { if (uf == 2) DGR_RENDER_FWD(4, 2); else DGR_RENDER_FWD(4, 1); }
@@ -458,7 +463,8 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
                    launch_k(render_bwd_kernel<PPL_, U_>, dim3((unsigned)grid_), dim3(kRenderThreads), smem_, st, false, H, W, IL.gx, \
                             reinterpret_cast<const unsigned *>(image + IL.off_order), &work->n_nonempty, bwd_next, g_two_ended.load(), dv->sms, co, \
                             reinterpret_cast<const uint2 *>(image + IL.off_oranges),                                       \
-                            reinterpret_cast<const Rec *>(binning + BL.off_rec), reinterpret_cast<const unsigned *>(binning + BL.off_ids), \
+                            reinterpret_cast<const Rec *>(binning + BL.off_rec), reinterpret_cast<const Rec *>(geom + GL.off_rec), \
+                            (const unsigned *)&work->lazy, reinterpret_cast<const unsigned *>(binning + BL.off_ids),          \
                             s->bg, reinterpret_cast<const float *>(image + IL.off_finalT),                                 \
                             reinterpret_cast<const unsigned *>(image + IL.off_ncontrib), gin->dL_dcolor, gin->dL_ddepth, gin->dL_dalpha, grad_rec)); \
     } while (0)

@@ -71,7 +71,8 @@ struct TileWork {                        // lives in image scratch (256 bytes, z
     unsigned n_nonempty;                 // tiles with at least one instance = the leading entries of tile_order
     unsigned long long fwd_next;         // work counter of the persistent forward render kernel (zeroed by the metadata block)
     unsigned cost_bpt;                   // backward items per tile the forward grouped its measured costs for (0: none)
-    unsigned pad[3];
+    unsigned lazy;                       // 1: the forward staged its records by id (no sorted record copy exists): the backward follows
+    unsigned pad[2];
     unsigned cls_count[kCostClasses];    // backward work items per measured-cost class (filled by the forward render kernel)
 };
 static_assert(sizeof(TileWork) <= 256, "TileWork");
@@ -295,7 +296,8 @@ struct SortSmem {
 // in flight per SM.
 template <int THREADS, int CAP, int NBK>
 __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long long *__restrict__ keys, const Rec *__restrict__ rec,
-                                                 unsigned *__restrict__ ids_sorted, Rec *__restrict__ rec_sorted, unsigned char *smem) {
+                                                 unsigned *__restrict__ ids_sorted, Rec *__restrict__ rec_sorted, unsigned char *smem,
+                                                 const bool gather) {
     using SM = SortSmem<THREADS, CAP, NBK>;
     constexpr int KPT = (CAP + THREADS - 1) / THREADS;
     const int n = (int)(r.y - r.x);
@@ -307,9 +309,11 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
         for (int i = tid; i < n; i += THREADS) {
             const unsigned gid = (unsigned)(gk[i] & 0xffffffffull);
             ids_sorted[r.x + i] = gid;
-            const Rec *src = rec + gid;
-            Rec v; v.q0 = __ldg(&src->q0); v.q1 = __ldg(&src->q1); v.q2 = __ldg(&src->q2);
-            rec_sorted[r.x + i] = v;
+            if (gather) {
+                const Rec *src = rec + gid;
+                Rec v; v.q0 = __ldg(&src->q0); v.q1 = __ldg(&src->q1); v.q2 = __ldg(&src->q2);
+                rec_sorted[r.x + i] = v;
+            }
         }
         __syncthreads();
         return;
@@ -400,10 +404,12 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
         const unsigned gid = (unsigned)(kk & 0xffffffffull);
         const size_t pos = (size_t)r.x + s + rank;
         ids_sorted[pos] = gid;
-        const Rec *src = rec + gid;
-        const float4 g0 = ldg_f4_hint(&src->q0, pol_keep), g1 = ldg_f4_hint(&src->q1, pol_keep), g2 = ldg_f4_hint(&src->q2, pol_keep);
-        Rec *dst = rec_sorted + pos;
-        stg_f4_hint(&dst->q0, g0, pol_stream); stg_f4_hint(&dst->q1, g1, pol_stream); stg_f4_hint(&dst->q2, g2, pol_stream);
+        if (gather) {
+            const Rec *src = rec + gid;
+            const float4 g0 = ldg_f4_hint(&src->q0, pol_keep), g1 = ldg_f4_hint(&src->q1, pol_keep), g2 = ldg_f4_hint(&src->q2, pol_keep);
+            Rec *dst = rec_sorted + pos;
+            stg_f4_hint(&dst->q0, g0, pol_stream); stg_f4_hint(&dst->q1, g1, pol_stream); stg_f4_hint(&dst->q2, g2, pol_stream);
+        }
     }
 }
 
@@ -415,7 +421,7 @@ constexpr int kSortBigThreads = 1024, kSortBigCap = 12288, kSortBigBuckets = 204
 // in flight while a tile is being sorted.  Tiles beyond kSortSmallCap are left to the big-tile kernel.
 __global__ void __launch_bounds__(kSortSmallThreads, 4)
 tile_sort_gather_kernel(const TileWork *__restrict__ work, const uint2 *__restrict__ order_ranges, unsigned long long *__restrict__ keys,
-                        const Rec *__restrict__ rec, unsigned *__restrict__ ids_sorted, Rec *__restrict__ rec_sorted) {
+                        const Rec *__restrict__ rec, unsigned *__restrict__ ids_sorted, Rec *__restrict__ rec_sorted, int gather) {
     extern __shared__ __align__(16) unsigned char s_sort[];
     pdl_trigger();
     pdl_wait();
@@ -427,7 +433,7 @@ tile_sort_gather_kernel(const TileWork *__restrict__ work, const uint2 *__restri
         const uint2 rnext = inext < n_tiles ? __ldcg(order_ranges + inext) : make_uint2(0u, 0u);
         const int n = (int)(r.y - r.x);
         if (n > 0 && n <= kSortSmallCap)
-            sort_gather_tile<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>(r, keys, rec, ids_sorted, rec_sorted, s_sort);
+            sort_gather_tile<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>(r, keys, rec, ids_sorted, rec_sorted, s_sort, gather != 0);
         i = inext; r = rnext;
     }
 }
@@ -436,13 +442,13 @@ tile_sort_gather_kernel(const TileWork *__restrict__ work, const uint2 *__restri
 __global__ void __launch_bounds__(kSortBigThreads)
 tile_sort_gather_big_kernel(const TileWork *__restrict__ work, const unsigned *__restrict__ big_list, const uint2 *__restrict__ ranges,
                             unsigned long long *__restrict__ keys, const Rec *__restrict__ rec, unsigned *__restrict__ ids_sorted,
-                            Rec *__restrict__ rec_sorted) {
+                            Rec *__restrict__ rec_sorted, int gather) {
     extern __shared__ __align__(16) unsigned char s_sort[];
     pdl_trigger();
     pdl_wait();
     const unsigned nb = work->n_big;
     for (unsigned i = blockIdx.x; i < nb; i += gridDim.x)
-        sort_gather_tile<kSortBigThreads, kSortBigCap, kSortBigBuckets>(ranges[big_list[i]], keys, rec, ids_sorted, rec_sorted, s_sort);
+        sort_gather_tile<kSortBigThreads, kSortBigCap, kSortBigBuckets>(ranges[big_list[i]], keys, rec, ids_sorted, rec_sorted, s_sort, gather != 0);
 }
 
 }  // namespace dgr

@@ -89,6 +89,25 @@ __device__ __forceinline__ void ring_issue(WarpRing &rg, int seq, const Rec *src
     mbar_expect_tx(&rg.full[st], bytes);
     tma_bulk_g2s(&rg.rec[st][0], src, bytes, &rg.full[st]);
 }
+// warp-wide: start the copy of list chunk `chunk` (records [chunk*32, chunk*32 + cnt) of the tile's depth-sorted list) into the
+// stage of sequence number `seq`.  lazy = false: the records were gathered into sorted order by the sort kernel — one
+// contiguous bulk copy (lane 0).  lazy = true: only the sorted Gaussian ids exist; every lane copies ITS record (48 bytes,
+// one cp.async.bulk each, all completing on the stage's mbarrier) straight from the per-Gaussian record array — the sort
+// kernel then moves 12 instead of 108 bytes per instance and records beyond the end of the walked lists are never touched.
+// (tools/tma_gather_probe.cu: 78 ns against 21 ns per 32-record chunk per SM, so the gather pays off where most of every
+// list is never walked or where the sort kernel is the long pole — the forward decides per call, `TileWork::lazy`.)
+__device__ __forceinline__ void ring_fill(WarpRing &rg, int seq, const Rec *src_sorted, const Rec *rec, unsigned my_id, int chunk, int cnt,
+                                          int lane, bool lazy) {
+    if (!lazy) {
+        if (lane == 0) ring_issue(rg, seq, src_sorted + (size_t)chunk * kChunk, cnt);
+    } else {
+        const int st = seq % kRing;
+        if (lane == 0) mbar_expect_tx(&rg.full[st], (uint32_t)cnt * (uint32_t)sizeof(Rec));
+        __syncwarp();
+        if (lane < cnt) tma_bulk_g2s(&rg.rec[st][lane], rec + my_id, (uint32_t)sizeof(Rec), &rg.full[st]);
+    }
+}
+
 // all lanes: wait for the chunk of sequence number `seq`, returns its stage
 __device__ __forceinline__ int ring_wait(WarpRing &rg, RingState &rs, int seq) {
     const int st = seq % kRing;
@@ -141,8 +160,9 @@ template <int PPL, int U>
 __global__ void __launch_bounds__(kRenderThreads)
 render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const uint2 *__restrict__ order_ranges,
                   const unsigned *__restrict__ n_tiles_nonempty, unsigned n_items, unsigned long long *__restrict__ work_next,
-                  int two_ended, int sms, CostOrder co,
-                  const Rec *__restrict__ rec_sorted, const float *__restrict__ bg, float *__restrict__ out_color,
+                  int two_ended, int sms, CostOrder co, int lazy_gather, unsigned *__restrict__ lazy_note,
+                  const Rec *__restrict__ rec_sorted, const Rec *__restrict__ rec, const unsigned *__restrict__ ids_sorted,
+                  const float *__restrict__ bg, float *__restrict__ out_color,
                   float *__restrict__ out_depth, float *__restrict__ out_alpha, unsigned *__restrict__ n_contrib,
                   float *__restrict__ final_T) {
     using ST = SubTile<PPL>;
@@ -163,6 +183,8 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     const unsigned warp_global = blockIdx.x * kRenderWarps + (threadIdx.x >> 5), warps_total = gridDim.x * kRenderWarps;
     const bool costing = co.cost_acc != nullptr && PPL <= co.bwd_ppl;                 // forward sub-tiles nest in the backward's
     if (costing && blockIdx.x == 0 && threadIdx.x == 0) *co.cost_bpt = (unsigned)(8 / co.bwd_ppl);
+    const bool lazy = lazy_gather != 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *lazy_note = lazy ? 1u : 0u;             // the backward of this forward follows suit
     const bool light = two_ended && (((blockIdx.x / (unsigned)sms) + (threadIdx.x >> 5)) & 1u);
     bool queue_phase = true;
     unsigned item = 0, empty_next = n_queue + warp_global;
@@ -189,9 +211,18 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
         const int wx0 = ST::x0(tx, sub), wy0 = ST::y0(ty, sub);
         const int wx1 = wx0 + ST::kW - 1, wy1 = wy0 + ST::kH - 1;
 
+        const unsigned *ids = ids_sorted + range.x;
         rs.issued = 0; rs.waited = 0;
-        if (lane == 0)
-            for (; rs.issued < min(kRing, nchunks); rs.issued++) ring_issue(rg, rs.issued, src + (size_t)rs.issued * kChunk, min(kChunk, n - rs.issued * kChunk));
+        unsigned nid = 0;                                       // lazy: this lane's Gaussian id in the next chunk to be issued
+        {
+            unsigned id0[kRing];
+#pragma unroll
+            for (int k = 0; k < kRing; k++) id0[k] = (lazy && k * kChunk + lane < n) ? __ldg(ids + k * kChunk + lane) : 0u;
+            if (lazy && kRing * kChunk + lane < n) nid = __ldg(ids + kRing * kChunk + lane);
+#pragma unroll
+            for (int k = 0; k < kRing; k++)
+                if (k < nchunks) ring_fill(rg, k, src, rec, id0[k], k, min(kChunk, n - k * kChunk), lane, lazy);
+        }
         rs.issued = min(kRing, nchunks);
 
         float fx[PPL], fy[PPL], T[PPL], C0[PPL], C1[PPL], C2[PPL], D[PPL];
@@ -266,10 +297,11 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
 #pragma unroll
             for (int p = 0; p < PPL; p++) all_done = all_done && done[p];
             warp_done = __all_sync(0xffffffffu, all_done);      // (also orders every lane's reads of stage s before its re-use)
-            if (!warp_done && lane == 0 && rs.issued < nchunks) {
-                ring_issue(rg, rs.issued, src + (size_t)rs.issued * kChunk, min(kChunk, n - rs.issued * kChunk));
+            if (!warp_done && rs.issued < nchunks) {
+                ring_fill(rg, rs.issued, src, rec, nid, rs.issued, min(kChunk, n - rs.issued * kChunk), lane, lazy);
+                rs.issued++;
+                if (lazy && rs.issued * kChunk + lane < n) nid = __ldg(ids + rs.issued * kChunk + lane);
             }
-            if (!warp_done && rs.issued < nchunks) rs.issued++;
         }
         // never move on (or leave) with a bulk copy in flight into this warp's ring
         for (int c = rs.waited; c < rs.issued; c++) ring_wait(rg, rs, c);
@@ -334,7 +366,8 @@ template <int PPL, int U>
 __global__ void __launch_bounds__(kRenderThreads)
 render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const unsigned *__restrict__ n_tiles_nonempty,
                   unsigned long long *__restrict__ work_next, int two_ended, int sms, CostOrder co, const uint2 *__restrict__ order_ranges,
-                  const Rec *__restrict__ rec_sorted, const unsigned *__restrict__ ids_sorted, const float *__restrict__ bg,
+                  const Rec *__restrict__ rec_sorted, const Rec *__restrict__ rec, const unsigned *__restrict__ lazy_note,
+                  const unsigned *__restrict__ ids_sorted, const float *__restrict__ bg,
                   const float *__restrict__ final_T, const unsigned *__restrict__ n_contrib,
                   const float *__restrict__ gC, const float *__restrict__ gD, const float *__restrict__ gA,
                   float *__restrict__ grad_rec) {
@@ -352,6 +385,7 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     ring_init(rg, rs, lane);
     // work list: the measured-cost classes of the forward (heaviest class first) when it grouped its costs for this sub-tile
     // shape, else every sub-tile of the non-empty tiles in population order
+    const bool lazy = __ldcg(lazy_note) != 0u;                      // how the forward of this backward staged its records
     const bool by_cost = co.cost_acc != nullptr && __ldcg(co.cost_bpt) == (unsigned)ST::kPerTile;
     unsigned cum_end = 0;                                            // lane L: items in classes kCostClasses-1 .. kCostClasses-1-L
     if (by_cost) {
@@ -414,11 +448,18 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
         const unsigned *ids = ids_sorted + range.x;
         // sequence number k handles chunk nchunks-1-k (back to front)
         rs.issued = 0; rs.waited = 0;
-        if (lane == 0)
-            for (; rs.issued < min(kRing, nchunks); rs.issued++) {
-                const int c = nchunks - 1 - rs.issued;
-                ring_issue(rg, rs.issued, src + (size_t)c * kChunk, min(kChunk, n - c * kChunk));
+        unsigned nid = 0;                                       // lazy: this lane's Gaussian id in the next chunk to be issued
+        {
+            unsigned id0[kRing];
+#pragma unroll
+            for (int k = 0; k < kRing; k++) { const int c = nchunks - 1 - k; id0[k] = (lazy && c >= 0 && c * kChunk + lane < n) ? __ldg(ids + c * kChunk + lane) : 0u; }
+            if (lazy && nchunks > kRing) nid = __ldg(ids + (size_t)(nchunks - 1 - kRing) * kChunk + lane);
+#pragma unroll
+            for (int k = 0; k < kRing; k++) {
+                const int c = nchunks - 1 - k;
+                if (c >= 0) ring_fill(rg, k, src, rec, id0[k], c, min(kChunk, n - c * kChunk), lane, lazy);
             }
+        }
         rs.issued = min(kRing, nchunks);
 
         // parked-record bookkeeping: lane L < kBatch owns slot L (centre relative to the sub-tile origin, Gaussian id)
@@ -536,11 +577,10 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
             }
             __syncwarp();                                       // every lane has left stage s
             if (rs.issued < nchunks) {
-                if (lane == 0) {
-                    const int c2 = nchunks - 1 - rs.issued;
-                    ring_issue(rg, rs.issued, src + (size_t)c2 * kChunk, min(kChunk, n - c2 * kChunk));
-                }
+                const int c2 = nchunks - 1 - rs.issued;
+                ring_fill(rg, rs.issued, src, rec, nid, c2, min(kChunk, n - c2 * kChunk), lane, lazy);
                 rs.issued++;
+                if (lazy && rs.issued < nchunks) nid = __ldg(ids + (size_t)(nchunks - 1 - rs.issued) * kChunk + lane);
             }
         }
         if (nslots > 0) flush();

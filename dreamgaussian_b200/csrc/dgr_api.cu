@@ -199,7 +199,7 @@ std::atomic<int> g_ppl_fwd{1}, g_ppl_bwd{1}, g_u_fwd{0}, g_u_bwd{0};      // u =
 std::atomic<bool> g_no_order{false};
 std::atomic<int> g_two_ended{0};
 std::atomic<int> g_cost_order{1};
-std::atomic<int> g_lazy{0};            // record staging of the render kernels: 0 = by id when the caller expects big tiles, 1 = always sorted copy, 2 = always by id      // backward work ordered by the cost the forward measured (dgr_render.cuh)       // work queue of the render kernels consumed from both ends (dgr_render.cuh)
+std::atomic<int> g_lazy{0};            // record staging of the render kernels: 0 = by id when the sorted copy would exceed 2x L2, 1 = always sorted copy, 2 = always by id      // backward work ordered by the cost the forward measured (dgr_render.cuh)       // work queue of the render kernels consumed from both ends (dgr_render.cuh)
 std::atomic<int> g_cta_fwd{0}, g_cta_bwd{0};   // persistent CTAs per SM of the render kernels (0 = as many as fit)
 
 using SmS = SortSmem<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>;
@@ -210,6 +210,7 @@ using SmB = SortSmem<kSortBigThreads, kSortBigCap, kSortBigBuckets>;
 struct DevInfo {
     bool ready = false;
     int sms = 148;
+    size_t l2_bytes = 126u << 20;
     int big_grid = 148;               // big-tile sorter: one CTA per SM
     std::map<const void *, int> grids;   // persistent (occupancy x SMs) grid of every render kernel instantiation used so far
 };
@@ -226,6 +227,8 @@ DevInfo *dev_info() {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) d.sms = n;
     d.big_grid = d.sms;
+    int l2 = 0;
+    if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) == cudaSuccess && l2 > 0) d.l2_bytes = (size_t)l2;
     cudaError_t e = cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileSmem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sort_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmS::bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sort_gather_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmB::bytes);
@@ -380,8 +383,12 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
             DGR_CUDA(cudaMemcpyAsync(counts_host, geom, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         if (count_ready_event) DGR_CUDA(cudaEventRecord((cudaEvent_t)count_ready_event, st));
     }
+    // Record staging of the render kernels.  A sorted copy of the records (written by the sort kernel, read with one contiguous
+    // bulk-TMA copy per 32 records) is the fast path while that copy lives in L2; once it is several times the L2 size the
+    // sort kernel's gather + write becomes the long pole (2M / 1600^2: 457 vs 164 us) and staging by id wins although a
+    // chunk then takes 32 small bulk copies (B200: 78 vs 21 ns per chunk per SM, profiles/r2_tma_gather_probe.txt).
     const int lz = g_lazy.load();
-    const bool lazy = lz == 2 || (lz == 0 && (flags & DGR_FLAG_BIG_TILES));
+    const bool lazy = lz == 2 || (lz == 0 && (size_t)capacity * sizeof(Rec) > 2 * dv->l2_bytes);
     if (g->P > 0 && capacity > 0) {
         const int sort_grid = min(tiles, persistent_grid(dv, tile_sort_gather_kernel, kSortSmallThreads, SmS::bytes));
         DGR_KERNEL("tile_sort_gather", st, s->debug,

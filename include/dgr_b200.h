@@ -127,10 +127,16 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom, 
                        uint64_t capacity_instances, void *image, const DgrImages *out, int32_t flags,
                        uint64_t *counts_host, uint64_t ticket, void *count_ready_event, void *stream);
 
-/* Tuning knobs (process-wide; results do not depend on them): pixels per lane of the forward / backward render
- * kernels (1, 2 or 4; the backward has 1 and 2); tile_order: bit 3 (value 8) turns OFF programmatic dependent launches
- * (A/B switch; the environment variable DGR_PDL=0 does the same); the other bits are accepted and ignored (the persistent
- * render kernels always pull work heaviest tile first). */
+/* Tuning knobs (process-wide atomics; results do not depend on them beyond the summation order of the gradient atomics):
+ * pixels per lane of the forward / backward render kernels (1, 2 or 4; the backward has 1 and 2) and a bit field:
+ *   bit 3        programmatic dependent launches OFF (the environment variable DGR_PDL=0 does the same)
+ *   bits 4-6     hits the forward evaluates together (1, 2, 4; 0 = default)      bits 8-10   the same for the backward
+ *   bits 12-15   persistent CTAs per SM of the forward render kernel (0 = as many as fit)     bits 16-19   backward
+ *   bit 20       render work queue consumed from both ends (experiment, measured slower)
+ *   bit 21       backward work in tile-population order instead of the cost the forward measured
+ *   bits 22-23   record staging of the render kernels: 0 = automatic (by Gaussian id when the sorted copy would exceed twice
+ *                the L2 size), 1 = always the sorted copy, 2 = always by id
+ * the other bits are accepted and ignored. */
 int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order);
 
 /* Thin cudaEvent wrappers so a host without the CUDA runtime headers (ctypes, cgo ...) can use the protocol above. */

@@ -9,7 +9,7 @@ import os
 from . import build as _build
 
 c_f32p = ctypes.c_void_p  # device pointers travel as integers
-ABI_VERSION = 3          # include/dgr_b200.h DGR_ABI_VERSION
+ABI_VERSION = 4          # include/dgr_b200.h DGR_ABI_VERSION
 
 
 class DgrSettings(ctypes.Structure):
@@ -54,14 +54,20 @@ class DgrGaussianGrads(ctypes.Structure):
         ("dL_dopacities", c_f32p), ("dL_dscales", c_f32p), ("dL_drotations", c_f32p), ("dL_dcov3D_precomp", c_f32p),
         ("accumulate", ctypes.c_int32),
         ("dL_dshs_rest", c_f32p), ("xyz_gradient_accum", c_f32p), ("denom", c_f32p), ("max_radii2D", c_f32p),
+        ("push", ctypes.c_void_p),
     ]
+
+
+class DgrPeerPush(ctypes.Structure):
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("gaussians_per_owner", ctypes.c_int64),
+                ("delta_floats", ctypes.c_int64 * 16)]
 
 
 EXPORTS = (
     "dgr_abi_version", "dgr_last_error", "dgr_launch_count", "dgr_reset_launch_count",
     "dgr_geom_bytes", "dgr_image_bytes", "dgr_binning_bytes",
     "dgr_forward_preprocess", "dgr_forward_render", "dgr_backward", "dgr_mark_visible", "dgr_debug_geom",
-    "dgr_profile_enable", "dgr_profile_collect", "dgr_event_create", "dgr_event_synchronize", "dgr_event_destroy", "dgr_set_tuning", "dgr_peer_allreduce", "dgr_peer_flag_bytes", "dgr_knn_scratch_bytes", "dgr_dist_cuda2", "dgr_fields_scratch_bytes", "dgr_extract_fields", "dgr_adam_step", "dgr_densify_scratch_bytes", "dgr_densify_plan", "dgr_densify_apply",
+    "dgr_profile_enable", "dgr_profile_collect", "dgr_event_create", "dgr_event_synchronize", "dgr_event_destroy", "dgr_set_tuning", "dgr_peer_allreduce", "dgr_peer_flag_bytes", "dgr_peer_reduce_staged", "dgr_peer_push_flat", "dgr_knn_scratch_bytes", "dgr_dist_cuda2", "dgr_fields_scratch_bytes", "dgr_extract_fields", "dgr_adam_step", "dgr_densify_scratch_bytes", "dgr_densify_plan", "dgr_densify_apply",
 )
 
 _lib = None
@@ -101,6 +107,10 @@ def load():
     lib.dgr_forward_preprocess.argtypes = [ctypes.POINTER(DgrSettings), ctypes.POINTER(DgrGaussians), vp, vp, vp, vp]
     lib.dgr_peer_allreduce.restype = ctypes.c_int
     lib.dgr_peer_allreduce.argtypes = [vp, i32, i32, u64, u64, vp, ctypes.c_uint32, vp]
+    lib.dgr_peer_reduce_staged.restype = ctypes.c_int
+    lib.dgr_peer_reduce_staged.argtypes = [vp, vp, ctypes.c_int64, i32, vp, vp, u64, u64, u64, vp, ctypes.c_uint32, vp]
+    lib.dgr_peer_push_flat.restype = ctypes.c_int
+    lib.dgr_peer_push_flat.argtypes = [vp, vp, ctypes.c_int64, i32, vp, vp, vp]
     lib.dgr_peer_flag_bytes.restype = ctypes.c_size_t
     lib.dgr_set_tuning.restype = ctypes.c_int
     lib.dgr_set_tuning.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]

@@ -152,11 +152,17 @@ template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
 void launch_pre_bwd(const DgrSettings *s, const DgrGaussians *g, const int *radii, const unsigned *touched, const float *grad_rec,
                     const DgrGaussianGrads *o, cudaStream_t st) {
     const int nb = (g->P + kPreThreads - 1) / kPreThreads;
+    PeerPush push;
+    memset(&push, 0, sizeof(push));
+    if (o->push) {
+        push.per = (int)o->push->gaussians_per_owner;
+        for (int w = 0; w < o->push->world && w < kMaxPeers; w++) push.delta[w] = o->push->delta_floats[w];
+    }
     launch_k(preprocess_bwd_kernel<DEG, HAS_SH, HAS_COV, RAW>, dim3(nb), dim3(kPreThreads), 0, st, true,
         g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
         s->campos, g->means3D, g->shs, g->shs_rest, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii, touched, grad_rec,
         o->dL_dmeans3D, o->dL_dmeans2D, o->dL_dshs, o->dL_dcolors_precomp, o->dL_dopacities, o->dL_dscales, o->dL_drotations,
-        o->dL_dcov3D_precomp, o->dL_dshs_rest, o->xyz_gradient_accum, o->denom, o->max_radii2D, o->accumulate);
+        o->dL_dcov3D_precomp, o->dL_dshs_rest, o->xyz_gradient_accum, o->denom, o->max_radii2D, o->accumulate, push);
 }
 
 #define DGR_DISPATCH(FN, ...)                                                                              \
@@ -407,22 +413,43 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
         co.cls_items = reinterpret_cast<unsigned *>(image + IL.off_clsitems); co.cost_bpt = &work->cost_bpt;
         co.tiles = tiles; co.bwd_ppl = g_ppl_bwd.load();
     }
-#define DGR_RENDER_FWD(PPL_, U_)                                                                                \
+#define DGR_RENDER_FWD_L(PPL_, U_, L_)                                                                          \
     do {                                                                                                        \
         const int items_ = tiles * SubTile<PPL_>::kPerTile;                                                     \
-        int grid_ = min(persistent_grid(dv, render_fwd_kernel<PPL_, U_>, kRenderThreads, 0), (items_ + kRenderWarps - 1) / kRenderWarps); \
+        int grid_ = min(persistent_grid(dv, render_fwd_kernel<PPL_, U_, L_>, kRenderThreads, 0), (items_ + kRenderWarps - 1) / kRenderWarps); \
         if (g_cta_fwd.load() > 0) grid_ = min(grid_, g_cta_fwd.load() * dv->sms);                               \
         DGR_KERNEL("render_fwd", st, s->debug,                                                                  \
-                   launch_k(render_fwd_kernel<PPL_, U_>, dim3((unsigned)grid_), dim3(kRenderThreads), 0, st, true, H, W, IL.gx,   \
+                   launch_k(render_fwd_kernel<PPL_, U_, L_>, dim3((unsigned)grid_), dim3(kRenderThreads), 0, st, true, H, W, IL.gx,   \
                             (const unsigned *)tile_order, reinterpret_cast<const uint2 *>(image + IL.off_oranges),         \
-                            (const unsigned *)&work->n_nonempty, (unsigned)items_, &work->fwd_next, g_two_ended.load(), dv->sms, co, lazy ? 1 : 0, \
+                            (const unsigned *)&work->n_nonempty, (unsigned)items_, &work->fwd_next, g_two_ended.load(), dv->sms, co, \
                             &work->lazy, (const Rec *)recs, rec, (const unsigned *)ids,                                      \
                             s->bg, out->color, out->depth, out->alpha, n_contrib, final_T));                     \
     } while (0)
-    if (ppl == 4) { if (uf == 2) DGR_RENDER_FWD(4, 2); else DGR_RENDER_FWD(4, 1); }
-    else if (ppl == 2) { if (uf == 1) DGR_RENDER_FWD(2, 1); else if (uf == 4) DGR_RENDER_FWD(2, 4); else DGR_RENDER_FWD(2, 2); }
-    else { if (uf == 1) DGR_RENDER_FWD(1, 1); else if (uf == 2) DGR_RENDER_FWD(1, 2); else DGR_RENDER_FWD(1, 4); }
+#define DGR_RENDER_FWD(PPL_, U_) do { if (lazy) DGR_RENDER_FWD_L(PPL_, U_, true); else DGR_RENDER_FWD_L(PPL_, U_, false); } while (0)
+    if (ppl == 4) DGR_RENDER_FWD(4, 1);
+    else if (ppl == 2) DGR_RENDER_FWD(2, 2);
+    else { if (uf == 4) DGR_RENDER_FWD(1, 4); else DGR_RENDER_FWD(1, 1); }      // default <1,1>: 58 registers, 8 CTAs per SM, no spill
+#undef DGR_RENDER_FWD_L
 #undef DGR_RENDER_FWD
+    return 0;
+}
+
+static int check_push(const DgrPeerPush *p, int64_t P) {
+    if (!p) return 0;
+    if (p->world < 1 || p->world > kMaxPeers || p->rank < 0 || p->rank >= p->world) return fail(-1, "push: bad world / rank");
+    if (p->gaussians_per_owner <= 0 || p->gaussians_per_owner % kPreThreads != 0) return fail(-1, "push: gaussians_per_owner must be a positive multiple of 256");
+    if (p->gaussians_per_owner * p->world < P) return fail(-1, "push: gaussians_per_owner * world < P");
+    if (p->delta_floats[p->rank] != 0) return fail(-1, "push: delta_floats[rank] must be 0");
+    return 0;
+}
+
+static int flat_segs(int32_t n_seg, const int64_t *seg_off, const int32_t *seg_stride, FlatSegs *out) {
+    if (n_seg < 1 || n_seg > 8 || !seg_off || !seg_stride) return fail(-1, "1..8 flat segments expected");
+    out->n = n_seg;
+    for (int k = 0; k < n_seg; k++) {
+        if (seg_off[k] < 0 || seg_stride[k] < 1) return fail(-1, "bad flat segment");
+        out->off[k] = seg_off[k]; out->stride[k] = seg_stride[k];
+    }
     return 0;
 }
 
@@ -436,6 +463,7 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
     if (!geom_v || !image_v || !gin || !gout) return fail(-1, "NULL argument");
     if (g->P == 0) return 0;
     if (!radii) return fail(-1, "radii is NULL");
+    if (int e = check_push(gout->push, g->P)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     char *geom = (char *)geom_v;
     const char *binning = (const char *)binning_v, *image = (const char *)image_v;
@@ -460,14 +488,14 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
             co.cls_items = const_cast<unsigned *>(reinterpret_cast<const unsigned *>(image + IL.off_clsitems)); co.cost_bpt = &wk->cost_bpt;
             co.tiles = tiles; co.bwd_ppl = ppl == 1 ? 1 : 2;
         }
-#define DGR_RENDER_BWD(PPL_, U_)                                                                                              \
+#define DGR_RENDER_BWD_L(PPL_, U_, L_)                                                                                        \
     do {                                                                                                                   \
         const size_t smem_ = sizeof(BwdSmem<PPL_>) * kRenderWarps;                                                         \
-        int grid_ = min(persistent_grid(dv, render_bwd_kernel<PPL_, U_>, kRenderThreads, smem_),                           \
+        int grid_ = min(persistent_grid(dv, render_bwd_kernel<PPL_, U_, L_>, kRenderThreads, smem_),                       \
                         (tiles * SubTile<PPL_>::kPerTile + kRenderWarps - 1) / kRenderWarps);                              \
         if (g_cta_bwd.load() > 0) grid_ = min(grid_, g_cta_bwd.load() * dv->sms);                                          \
         DGR_KERNEL("render_bwd", st, s->debug,                                                                             \
-                   launch_k(render_bwd_kernel<PPL_, U_>, dim3((unsigned)grid_), dim3(kRenderThreads), smem_, st, false, H, W, IL.gx, \
+                   launch_k(render_bwd_kernel<PPL_, U_, L_>, dim3((unsigned)grid_), dim3(kRenderThreads), smem_, st, false, H, W, IL.gx, \
                             reinterpret_cast<const unsigned *>(image + IL.off_order), &work->n_nonempty, bwd_next, g_two_ended.load(), dv->sms, co, \
                             reinterpret_cast<const uint2 *>(image + IL.off_oranges),                                       \
                             reinterpret_cast<const Rec *>(binning + BL.off_rec), reinterpret_cast<const Rec *>(geom + GL.off_rec), \
@@ -475,8 +503,13 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
                             s->bg, reinterpret_cast<const float *>(image + IL.off_finalT),                                 \
                             reinterpret_cast<const unsigned *>(image + IL.off_ncontrib), gin->dL_dcolor, gin->dL_ddepth, gin->dL_dalpha, grad_rec)); \
     } while (0)
-        if (ppl == 1) { if (ub == 2) DGR_RENDER_BWD(1, 2); else if (ub == 4) DGR_RENDER_BWD(1, 4); else DGR_RENDER_BWD(1, 1); }
-        else { if (ub == 2) DGR_RENDER_BWD(2, 2); else if (ub == 4) DGR_RENDER_BWD(2, 4); else DGR_RENDER_BWD(2, 1); }
+#define DGR_RENDER_BWD(PPL_, U_) do { if (lazy) DGR_RENDER_BWD_L(PPL_, U_, true); else DGR_RENDER_BWD_L(PPL_, U_, false); } while (0)
+        // the record staging follows the rule the forward applied to the same capacity (dgr_forward_render)
+        const int lz = g_lazy.load();
+        const bool lazy = lz == 2 || (lz == 0 && (size_t)capacity * sizeof(Rec) > 2 * dv->l2_bytes);
+        if (ppl == 1) { if (ub == 1) DGR_RENDER_BWD(1, 1); else DGR_RENDER_BWD(1, 2); }     // default <1,2> (in-pipeline sweep, profiles/r2_sweep.txt)
+        else { if (ub == 2) DGR_RENDER_BWD(2, 2); else DGR_RENDER_BWD(2, 1); }
+#undef DGR_RENDER_BWD_L
 #undef DGR_RENDER_BWD
     }
     DGR_KERNEL("preprocess_bwd", st, s->debug, DGR_DISPATCH(launch_pre_bwd, s, g, radii, reinterpret_cast<const unsigned *>(geom + GL.off_touched), grad_rec, gout, st));
@@ -514,6 +547,61 @@ int dgr_peer_allreduce(const uint64_t *peer_ptrs, int32_t world, int32_t rank, u
         if (bar) DGR_KERNEL("allreduce_p2p", st, 0, allreduce_p2p_kernel<true><<<grid, 512, 0, st>>>(pp, pf, epoch, world, rank, n4));
         else DGR_KERNEL("allreduce_p2p", st, 0, allreduce_p2p_kernel<false><<<grid, 512, 0, st>>>(pp, pf, epoch, world, rank, n4));
     }
+    return 0;
+}
+
+int dgr_peer_reduce_staged(const uint64_t *peer_ptrs, const DgrPeerPush *push, int64_t P, int32_t n_seg, const int64_t *seg_off,
+                           const int32_t *seg_stride, uint64_t stage_ptr, uint64_t padded_floats, uint64_t multicast_ptr,
+                           const uint64_t *peer_flag_ptrs, uint32_t epoch, void *stream) {
+    NvtxRange nvtx_("dgr_peer_reduce_staged");
+    if (!push || !peer_ptrs || !stage_ptr) return fail(-1, "NULL argument");
+    if (int e = check_push(push, P)) return e;
+    FlatSegs segs;
+    if (int e = flat_segs(n_seg, seg_off, seg_stride, &segs)) return e;
+    if (P <= 0 || P > 0x7fffffff) return fail(-1, "bad P");
+    const int world = push->world, rank = push->rank;
+    if (world == 1) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    DevInfo *dv = dev_info();
+    if (!dv) return -1;
+    size_t widest = 1;
+    for (int k = 0; k < segs.n; k++) widest = std::max(widest, (size_t)segs.stride[k]);
+    const size_t n4 = (size_t)push->gaussians_per_owner * widest / 4;                     // the longest segment loop (every segment uses the whole grid)
+    int grid = (int)((n4 + 512 * kUnroll - 1) / (512 * kUnroll));
+    if (grid > 4 * dv->sms) grid = 4 * dv->sms;
+    if (grid < 1) grid = 1;
+    PeerPtrs pp;
+    PeerFlags pf;
+    for (int w = 0; w < kMaxPeers; w++) {
+        pp.p[w] = w < world ? reinterpret_cast<float *>(peer_ptrs[w]) : nullptr;
+        pf.p[w] = (peer_flag_ptrs && w < world) ? reinterpret_cast<unsigned *>(peer_flag_ptrs[w]) : nullptr;
+    }
+    float *mc = reinterpret_cast<float *>(multicast_ptr);
+    const float *stage = reinterpret_cast<const float *>(stage_ptr);
+    if (peer_flag_ptrs)
+        DGR_KERNEL("reduce_staged", st, 0, reduce_staged_kernel<true><<<grid, 512, 0, st>>>(pp, mc, stage, (size_t)padded_floats, pf, epoch, world, rank, (int)P, (int)push->gaussians_per_owner, segs));
+    else
+        DGR_KERNEL("reduce_staged", st, 0, reduce_staged_kernel<false><<<grid, 512, 0, st>>>(pp, mc, stage, (size_t)padded_floats, pf, epoch, world, rank, (int)P, (int)push->gaussians_per_owner, segs));
+    return 0;
+}
+
+int dgr_peer_push_flat(const float *local, const DgrPeerPush *push, int64_t P, int32_t n_seg, const int64_t *seg_off,
+                       const int32_t *seg_stride, void *stream) {
+    NvtxRange nvtx_("dgr_peer_push_flat");
+    if (!push || !local) return fail(-1, "NULL argument");
+    if (int e = check_push(push, P)) return e;
+    FlatSegs segs;
+    if (int e = flat_segs(n_seg, seg_off, seg_stride, &segs)) return e;
+    if (P <= 0 || P > 0x7fffffff) return fail(-1, "bad P");
+    if (push->world == 1) return 0;
+    DevInfo *dv = dev_info();
+    if (!dv) return -1;
+    PeerPush pd;
+    memset(&pd, 0, sizeof(pd));
+    pd.per = (int)push->gaussians_per_owner;
+    for (int w = 0; w < push->world; w++) pd.delta[w] = push->delta_floats[w];
+    cudaStream_t st = (cudaStream_t)stream;
+    DGR_KERNEL("push_flat", st, 0, push_flat_kernel<<<2 * dv->sms, 512, 0, st>>>(local, pd, push->world, push->rank, (int)P, segs));
     return 0;
 }
 

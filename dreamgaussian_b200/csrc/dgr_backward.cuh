@@ -33,41 +33,98 @@ __device__ __forceinline__ void sh_dbasis(int k, float x, float y, float z, floa
     }
 }
 
-__device__ __forceinline__ void store_acc(float *p, float v, bool acc) { *p = acc ? (*p + v) : v; }
+// ---- output stage ---------------------------------------------------------------------------------------------------------------
+// Every gradient segment is [P, K] row-major, so the 32 rows of a warp are ONE contiguous run of 32 K floats.  Each lane drops its
+// K values into the warp's shared-memory image of that run and the warp writes the run back with 16-byte stores on consecutive
+// addresses (one store instruction for a [32, 3] block instead of three strided ones; full 32-byte sectors, which is what matters
+// when the destination is another GPU's memory behind NVLink).
+//   acc:        add to what the LOCAL buffer holds (several views -> one gradient);
+//   delta != 0: the result goes to the same element of this rank's slot in the owner rank's staging area (PeerPush) instead of
+//               back to the local buffer.
+constexpr int kOut3D = 0, kOut2D = 96, kOutOp = 192, kOutScale = 224, kOutRot = 320, kOutCov = 448, kOutCol = 640;    // float offsets per warp
+constexpr int kShStrideVec = 28, kShStrideScalar = 25;
+constexpr int kStageFloats = 32 * kShStrideVec;               // per warp: >= kOutCol + 32 * 3
 
-// Coalesced write of the SH gradient rows of one warp's 32 Gaussians.  Each lane owns one row (3M floats, of which
-// the first 3*NB are bs[k]*gr[ch] and the rest zero); writing them directly would make every store instruction touch
-// 32 different cache lines.  Instead the rows are transposed through shared memory in chunks of 24 floats
-// (row stride 25 words: conflict-free) and written back with consecutive lanes on consecutive addresses.
+__device__ __forceinline__ void warp_flush(float *seg, int K, long long delta, int row_base, int nrows, bool acc, const float *ws) {
+    if (!seg) return;
+    const int lane = threadIdx.x & 31;
+    float *loc = seg + (size_t)row_base * K;
+    float *dst = loc + delta;
+    const int n = nrows * K;
+    int done = 0;
+    if ((((size_t)loc | (size_t)dst) & 15) == 0) {
+        const int n4 = n >> 2;
+        for (int i = lane; i < n4; i += 32) {
+            float4 x = reinterpret_cast<const float4 *>(ws)[i];
+            if (acc) { const float4 o = reinterpret_cast<const float4 *>(loc)[i]; x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w; }
+            reinterpret_cast<float4 *>(dst)[i] = x;
+        }
+        done = n4 << 2;
+    }
+    for (int i = done + lane; i < n; i += 32) {
+        float x = ws[i];
+        if (acc) x += loc[i];
+        dst[i] = x;
+    }
+}
+
+// SH gradient rows of one warp's 32 Gaussians.  Each lane owns one row (3M floats, of which the first 3*NB are bs[k]*gr[ch] and the
+// rest zero).  The rows go through shared memory in chunks of 24 floats; a chunk leaves as 16-byte stores, 96 contiguous bytes
+// per row, when the row length is a multiple of 4 floats (row stride 28 words: conflict-free 16-byte accesses), else as 4-byte
+// stores with consecutive lanes on consecutive addresses (row stride 25 words).
 // FIRST = 1: the destination rows are GaussianModel._features_rest ([P, M-1, 3], coefficients 1 .. M-1).
 template <int DEG, int FIRST = 0>
 __device__ __forceinline__ void store_sh_grads(float *__restrict__ dL_dshs, int P, int M, const float (&bs)[16],
-                                               const float (&gr)[3], bool acc, float *stage /* [32*25] of this warp */) {
+                                               const float (&gr)[3], bool acc, float *stage /* [kStageFloats] of this warp */,
+                                               long long delta = 0) {
     constexpr int NB = (DEG + 1) * (DEG + 1) - FIRST;
     const int lane = threadIdx.x & 31;
     const int row_base = (int)(blockIdx.x * blockDim.x) + (int)(threadIdx.x & ~31u);
     const int nrows = min(32, P - row_base);
     if (nrows <= 0) return;
     const int rowlen = 3 * (M - FIRST);
+    const bool vec = (rowlen & 3) == 0 && ((((size_t)dL_dshs) | ((size_t)(dL_dshs + delta))) & 15) == 0;
 #pragma unroll
     for (int c = 0; c < 2; c++) {
         if (24 * c < rowlen) {
-#pragma unroll
-            for (int j = 0; j < 24; j++) {
-                const int f = 24 * c + j;                 // compile-time
-                const float v = (f / 3 < NB) ? bs[(f / 3 + FIRST) < 16 ? (f / 3 + FIRST) : 0] * gr[f % 3] : 0.f;
-                if (f < rowlen) stage[lane * 25 + j] = v;
-            }
-            __syncwarp();
             const int cw = min(24, rowlen - 24 * c);
-            const unsigned inv = (65536u + (unsigned)cw - 1u) / (unsigned)cw;      // exact idx / cw for idx < 32 * 24
-            for (int it = 0; it < cw; it++) {
-                const int idx = it * 32 + lane;
-                const int row = (int)(((unsigned)idx * inv) >> 16), col = idx - row * cw;
-                if (row < nrows) {
-                    float *dst = dL_dshs + (size_t)(row_base + row) * rowlen + 24 * c + col;
-                    const float v = stage[row * 25 + col];
-                    *dst = acc ? (*dst + v) : v;
+            if (vec) {
+#pragma unroll
+                for (int j4 = 0; j4 < 6; j4++) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int f = 24 * c + 4 * j4 + e;            // compile-time
+                        v[e] = (f / 3 < NB) ? bs[(f / 3 + FIRST) < 16 ? (f / 3 + FIRST) : 0] * gr[f % 3] : 0.f;
+                    }
+                    if (4 * j4 < cw) reinterpret_cast<float4 *>(stage + lane * kShStrideVec)[j4] = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                __syncwarp();
+                const int q = cw >> 2, total = nrows * q;
+                for (int i = lane; i < total; i += 32) {
+                    const int row = i / q, c4 = i - row * q;
+                    float4 x = *reinterpret_cast<const float4 *>(stage + row * kShStrideVec + 4 * c4);
+                    float *loc = dL_dshs + (size_t)(row_base + row) * rowlen + 24 * c + 4 * c4;
+                    if (acc) { const float4 o = *reinterpret_cast<const float4 *>(loc); x.x += o.x; x.y += o.y; x.z += o.z; x.w += o.w; }
+                    *reinterpret_cast<float4 *>(loc + delta) = x;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 24; j++) {
+                    const int f = 24 * c + j;                 // compile-time
+                    const float v = (f / 3 < NB) ? bs[(f / 3 + FIRST) < 16 ? (f / 3 + FIRST) : 0] * gr[f % 3] : 0.f;
+                    if (f < rowlen) stage[lane * kShStrideScalar + j] = v;
+                }
+                __syncwarp();
+                const unsigned inv = (65536u + (unsigned)cw - 1u) / (unsigned)cw;      // exact idx / cw for idx < 32 * 24
+                for (int it = 0; it < cw; it++) {
+                    const int idx = it * 32 + lane;
+                    const int row = (int)(((unsigned)idx * inv) >> 16), col = idx - row * cw;
+                    if (row < nrows) {
+                        float *dst = dL_dshs + (size_t)(row_base + row) * rowlen + 24 * c + col;
+                        const float v = stage[row * kShStrideScalar + col];
+                        dst[delta] = acc ? (*dst + v) : v;
+                    }
                 }
             }
             __syncwarp();
@@ -88,14 +145,20 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                       float *__restrict__ dL_dcolors, float *__restrict__ dL_dopacities, float *__restrict__ dL_dscales,
                       float *__restrict__ dL_drotations, float *__restrict__ dL_dcov3D, float *__restrict__ dL_dshs_rest,
                       float *__restrict__ xyz_gradient_accum, float *__restrict__ denom, float *__restrict__ max_radii2D,
-                      int accumulate) {
+                      int accumulate, PeerPush push) {
     __shared__ FrameConsts fc;
-    __shared__ float s_stage[HAS_SH ? (kPreThreads / 32) * 32 * 25 : 1];
+    __shared__ __align__(16) float s_stage[(kPreThreads / 32) * kStageFloats];
     load_frame(fc, viewmatrix, projmatrix, HAS_SH ? campos : nullptr);
     __syncthreads();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const bool acc = accumulate != 0;
     const bool in_range = g < P;
+    // gradient rows of Gaussians another rank owns go to that rank's staging slot (what the local buffer has accumulated over
+    // this rank's earlier views of the iteration + this view); every row is written then, culled Gaussians included
+    const long long delta = push.per > 0 ? push.delta[(blockIdx.x * blockDim.x) / (unsigned)push.per] : 0;
+    const bool pushing = delta != 0;
+    float *ws = s_stage + (threadIdx.x >> 5) * kStageFloats;        // this warp's output image (see warp_flush)
+    const int lane = threadIdx.x & 31;
     // every input of this Gaussian is requested up front (one memory round trip; none of it depends on the backward render)
     int radius_in = 0;
     unsigned touched_in = 0;
@@ -125,14 +188,13 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
 #pragma unroll
     for (int k = 0; k < 16; k++) bs[k] = 0.f;
 
-    if (in_range && !visible && !acc) {
-        if (dL_dmeans3D) { dL_dmeans3D[3 * (size_t)g] = 0.f; dL_dmeans3D[3 * (size_t)g + 1] = 0.f; dL_dmeans3D[3 * (size_t)g + 2] = 0.f; }
-        if (dL_dmeans2D) { dL_dmeans2D[3 * (size_t)g] = 0.f; dL_dmeans2D[3 * (size_t)g + 1] = 0.f; dL_dmeans2D[3 * (size_t)g + 2] = 0.f; }
-        if (!HAS_SH && dL_dcolors) { dL_dcolors[3 * (size_t)g] = 0.f; dL_dcolors[3 * (size_t)g + 1] = 0.f; dL_dcolors[3 * (size_t)g + 2] = 0.f; }
-        if (dL_dopacities) dL_dopacities[g] = 0.f;
-        if (!HAS_COV && dL_dscales) { dL_dscales[3 * (size_t)g] = 0.f; dL_dscales[3 * (size_t)g + 1] = 0.f; dL_dscales[3 * (size_t)g + 2] = 0.f; }
-        if (!HAS_COV && dL_drotations) { for (int k = 0; k < 4; k++) dL_drotations[4 * (size_t)g + k] = 0.f; }
-        if (HAS_COV && dL_dcov3D) { for (int k = 0; k < 6; k++) dL_dcov3D[6 * (size_t)g + k] = 0.f; }
+    if (!visible) {                                                 // culled (or past the end): a zero row in every segment
+#pragma unroll
+        for (int k = 0; k < 3; k++) { ws[kOut3D + 3 * lane + k] = 0.f; ws[kOut2D + 3 * lane + k] = 0.f; ws[kOutScale + 3 * lane + k] = 0.f; }
+        ws[kOutOp + lane] = 0.f;
+        *reinterpret_cast<float4 *>(ws + kOutRot + 4 * lane) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (HAS_COV) { for (int k = 0; k < 6; k++) ws[kOutCov + 6 * lane + k] = 0.f; }
+        if (!HAS_SH) { for (int k = 0; k < 3; k++) ws[kOutCol + 3 * lane + k] = 0.f; }
     }
     if (visible) {
         float R[9];
@@ -174,10 +236,7 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
         float dmean[3] = { 0.f, 0.f, 0.f };
         // (1) mean_px through the full projection; reported means2D grad is in NDC units
         const float gndx = gpx * 0.5f * (float)W, gndy = gpy * 0.5f * (float)H;
-        if (dL_dmeans2D) {
-            store_acc(dL_dmeans2D + 3 * (size_t)g, gndx, acc); store_acc(dL_dmeans2D + 3 * (size_t)g + 1, gndy, acc);
-            if (!acc) dL_dmeans2D[3 * (size_t)g + 2] = 0.f;
-        }
+        ws[kOut2D + 3 * lane] = gndx; ws[kOut2D + 3 * lane + 1] = gndy; ws[kOut2D + 3 * lane + 2] = 0.f;
         // densification bookkeeping of the training loop (gs_renderer.py:625-627, main.py:279-281), for visible Gaussians:
         // xyz_gradient_accum += |d L / d means2D[:, :2]| of THIS render, denom += 1, max_radii2D = max(max_radii2D, radii)
         if (xyz_gradient_accum) xyz_gradient_accum[g] += sqrtf(gndx * gndx + gndy * gndy);
@@ -214,11 +273,11 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
             }
             const float dot = dx * ddx + dy * ddy + dz * ddz;
             dmean[0] += (ddx - dx * dot) * il; dmean[1] += (ddy - dy * dot) * il; dmean[2] += (ddz - dz * dot) * il;
-        } else if (dL_dcolors) {
+        } else {
 #pragma unroll
-            for (int ch = 0; ch < 3; ch++) store_acc(dL_dcolors + 3 * (size_t)g + ch, g_rgb[ch], acc);
+            for (int ch = 0; ch < 3; ch++) ws[kOutCol + 3 * lane + ch] = g_rgb[ch];
         }
-        if (dL_dopacities) store_acc(dL_dopacities + g, RAW ? g_op * o * (1.f - o) : g_op, acc);     // sigmoid'
+        ws[kOutOp + lane] = RAW ? g_op * o * (1.f - o) : g_op;                                              // sigmoid'
 
         // (2) conic -> cov2D -> (Sigma, T = J Rwv)
         const float d2 = di * di;
@@ -256,16 +315,11 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
         const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + 2.f * fx * geo.tx * tz3 * dJ02 + 2.f * fy * geo.ty * tz3 * dJ12;
 #pragma unroll
         for (int k = 0; k < 3; k++) dmean[k] += fc.V[4 * k] * dtx + fc.V[4 * k + 1] * dty + fc.V[4 * k + 2] * dtz;
-        if (dL_dmeans3D) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) store_acc(dL_dmeans3D + 3 * (size_t)g + k, dmean[k], acc);
-        }
+        for (int k = 0; k < 3; k++) ws[kOut3D + 3 * lane + k] = dmean[k];
         if (HAS_COV) {
-            if (dL_dcov3D) {
-                float *out = dL_dcov3D + 6 * (size_t)g;
-                store_acc(out, dS[0], acc); store_acc(out + 1, 2.f * dS[1], acc); store_acc(out + 2, 2.f * dS[2], acc);
-                store_acc(out + 3, dS[4], acc); store_acc(out + 4, 2.f * dS[5], acc); store_acc(out + 5, dS[8], acc);
-            }
+            float *out = ws + kOutCov + 6 * lane;
+            out[0] = dS[0]; out[1] = 2.f * dS[1]; out[2] = 2.f * dS[2]; out[3] = dS[4]; out[4] = 2.f * dS[5]; out[5] = dS[8];
         } else {
             // Sigma = Mx Mx^T, Mx = R diag(s):  dL/dMx = 2 dS Mx
             float Mx[9];
@@ -284,11 +338,10 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                 float v = 0.f;
 #pragma unroll
                 for (int i = 0; i < 3; i++) { v += dM[3 * i + k] * R[3 * i + k]; dR[3 * i + k] = dM[3 * i + k] * sv[k]; }
-                if (dL_dscales) store_acc(dL_dscales + 3 * (size_t)g + k, RAW ? v * sv[k] : v * scale_modifier, acc);     // exp' = exp
+                ws[kOutScale + 3 * lane + k] = RAW ? v * sv[k] : v * scale_modifier;                                   // exp' = exp
             }
-            if (dL_drotations) {
+            {
                 const float r = q.x, x = q.y, y = q.z, z = q.w;
-                float *out = dL_drotations + 4 * (size_t)g;
                 float dq[4];
                 dq[0] = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
                 dq[1] = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
@@ -299,18 +352,38 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                     dq[0] = (dq[0] - r * qd) * inv_qnorm; dq[1] = (dq[1] - x * qd) * inv_qnorm;
                     dq[2] = (dq[2] - y * qd) * inv_qnorm; dq[3] = (dq[3] - z * qd) * inv_qnorm;
                 }
-#pragma unroll
-                for (int k = 0; k < 4; k++) store_acc(out + k, dq[k], acc);
+                *reinterpret_cast<float4 *>(ws + kOutRot + 4 * lane) = make_float4(dq[0], dq[1], dq[2], dq[3]);
             }
         }
     }
-    if (HAS_SH && RAW) {
-        if (dL_dshs && in_range) {                // _features_dc gradient [P,1,3] (zero for culled Gaussians: bs = gr = 0)
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++) store_acc(dL_dshs + 3 * (size_t)g + ch, bs[0] * gr[ch], acc);
+    // ---- the warp's rows leave together (see warp_flush); rows past the end of the arrays are not written
+    __syncwarp();
+    {
+        const int row_base = (int)(blockIdx.x * blockDim.x) + (int)(threadIdx.x & ~31u);
+        const int nrows = min(32, P - row_base);
+        if (nrows > 0) {
+            warp_flush(dL_dmeans3D, 3, delta, row_base, nrows, acc, ws + kOut3D);
+            warp_flush(dL_dmeans2D, 3, delta, row_base, nrows, acc, ws + kOut2D);
+            warp_flush(dL_dopacities, 1, delta, row_base, nrows, acc, ws + kOutOp);
+            if (!HAS_COV) {
+                warp_flush(dL_dscales, 3, delta, row_base, nrows, acc, ws + kOutScale);
+                warp_flush(dL_drotations, 4, delta, row_base, nrows, acc, ws + kOutRot);
+            } else warp_flush(dL_dcov3D, 6, delta, row_base, nrows, acc, ws + kOutCov);
+            if (!HAS_SH) warp_flush(dL_dcolors, 3, delta, row_base, nrows, acc, ws + kOutCol);
         }
-        if (dL_dshs_rest && M > 1) store_sh_grads<DEG, 1>(dL_dshs_rest, P, M, bs, gr, acc, s_stage + (threadIdx.x >> 5) * (32 * 25));
-    } else if (HAS_SH && dL_dshs) store_sh_grads<DEG>(dL_dshs, P, M, bs, gr, acc, s_stage + (threadIdx.x >> 5) * (32 * 25));
+        __syncwarp();
+        if (HAS_SH && RAW) {
+            if (dL_dshs && nrows > 0) {           // _features_dc gradient [P,1,3] (zero for culled Gaussians: bs = gr = 0)
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) ws[3 * lane + ch] = bs[0] * gr[ch];
+                __syncwarp();
+                warp_flush(dL_dshs, 3, delta, row_base, nrows, acc, ws);
+                __syncwarp();
+            }
+            if (dL_dshs_rest && M > 1) store_sh_grads<DEG, 1>(dL_dshs_rest, P, M, bs, gr, acc, ws, delta);
+        } else if (HAS_SH && dL_dshs) store_sh_grads<DEG>(dL_dshs, P, M, bs, gr, acc, ws, delta);
+    }
+    if (pushing) __threadfence_system();          // the rows are in the owner's memory when this grid completes
 }
 
 }  // namespace dgr

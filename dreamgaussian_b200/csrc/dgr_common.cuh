@@ -113,6 +113,13 @@ struct ImageLayout {
 // ------------------------------------------------ PTX wrappers ------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Multi-GPU (view-sharded): the per-Gaussian backward can write the gradient rows of Gaussians OWNED by another
+// rank straight into that rank's staging area over NVLink (dgr_backward.cuh, dgr_collective.cuh).  delta[o] = distance in
+// floats from a local gradient address to the same element of this rank's slot at owner o (0 for o = this rank); Gaussian g
+// belongs to owner g / per (per is a multiple of the kernel's block size, so a block has one owner).  per = 0: off.
+constexpr int kMaxPeers = 16;
+struct PeerPush { long long delta[kMaxPeers]; int per; };
+
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

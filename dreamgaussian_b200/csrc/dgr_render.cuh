@@ -95,10 +95,11 @@ __device__ __forceinline__ void ring_issue(WarpRing &rg, int seq, const Rec *src
 // one cp.async.bulk each, all completing on the stage's mbarrier) straight from the per-Gaussian record array — the sort
 // kernel then moves 12 instead of 108 bytes per instance and records beyond the end of the walked lists are never touched.
 // (tools/tma_gather_probe.cu: 78 ns against 21 ns per 32-record chunk per SM, so the gather pays off where most of every
-// list is never walked or where the sort kernel is the long pole — the forward decides per call, `TileWork::lazy`.)
+// list is never walked or where the sort kernel is the long pole: a compile-time variant, chosen per call by the host.)
+template <bool LAZY>
 __device__ __forceinline__ void ring_fill(WarpRing &rg, int seq, const Rec *src_sorted, const Rec *rec, unsigned my_id, int chunk, int cnt,
-                                          int lane, bool lazy) {
-    if (!lazy) {
+                                          int lane) {
+    if (!LAZY) {
         if (lane == 0) ring_issue(rg, seq, src_sorted + (size_t)chunk * kChunk, cnt);
     } else {
         const int st = seq % kRing;
@@ -156,11 +157,13 @@ struct CostOrder {                       // image scratch pieces (all may be NUL
 // U = hits evaluated together: the alpha of a (pixel, record) pair does not depend on the compositing state, so the long
 // part of the dependent chain (shared-memory read -> quadratic form -> ex2) of U hitting records is in flight at once and
 // only the short T / colour update runs in sequence.  Same per-pixel operation order for every U: bit-identical images.
-template <int PPL, int U>
-__global__ void __launch_bounds__(kRenderThreads)
+// One-pixel-per-lane variants are held to 64 registers (8 CTAs per SM): measured 4-5 us per step at 100k / 800^2 against the
+// 72 registers ptxas picks on its own (A/B in profiles/r2_ab_variants.log).
+template <int PPL, int U, bool LAZY>
+__global__ void __launch_bounds__(kRenderThreads, PPL == 1 ? 8 : 1)
 render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const uint2 *__restrict__ order_ranges,
                   const unsigned *__restrict__ n_tiles_nonempty, unsigned n_items, unsigned long long *__restrict__ work_next,
-                  int two_ended, int sms, CostOrder co, int lazy_gather, unsigned *__restrict__ lazy_note,
+                  int two_ended, int sms, CostOrder co, unsigned *__restrict__ lazy_note,
                   const Rec *__restrict__ rec_sorted, const Rec *__restrict__ rec, const unsigned *__restrict__ ids_sorted,
                   const float *__restrict__ bg, float *__restrict__ out_color,
                   float *__restrict__ out_depth, float *__restrict__ out_alpha, unsigned *__restrict__ n_contrib,
@@ -183,8 +186,8 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     const unsigned warp_global = blockIdx.x * kRenderWarps + (threadIdx.x >> 5), warps_total = gridDim.x * kRenderWarps;
     const bool costing = co.cost_acc != nullptr && PPL <= co.bwd_ppl;                 // forward sub-tiles nest in the backward's
     if (costing && blockIdx.x == 0 && threadIdx.x == 0) *co.cost_bpt = (unsigned)(8 / co.bwd_ppl);
-    const bool lazy = lazy_gather != 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *lazy_note = lazy ? 1u : 0u;             // the backward of this forward follows suit
+    constexpr bool lazy = LAZY;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *lazy_note = LAZY ? 1u : 0u;             // (for the record; the host picks the backward's variant by the same rule)
     const bool light = two_ended && (((blockIdx.x / (unsigned)sms) + (threadIdx.x >> 5)) & 1u);
     bool queue_phase = true;
     unsigned item = 0, empty_next = n_queue + warp_global;
@@ -221,7 +224,7 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
             if (lazy && kRing * kChunk + lane < n) nid = __ldg(ids + kRing * kChunk + lane);
 #pragma unroll
             for (int k = 0; k < kRing; k++)
-                if (k < nchunks) ring_fill(rg, k, src, rec, id0[k], k, min(kChunk, n - k * kChunk), lane, lazy);
+                if (k < nchunks) ring_fill<LAZY>(rg, k, src, rec, id0[k], k, min(kChunk, n - k * kChunk), lane);
         }
         rs.issued = min(kRing, nchunks);
 
@@ -298,7 +301,7 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
             for (int p = 0; p < PPL; p++) all_done = all_done && done[p];
             warp_done = __all_sync(0xffffffffu, all_done);      // (also orders every lane's reads of stage s before its re-use)
             if (!warp_done && rs.issued < nchunks) {
-                ring_fill(rg, rs.issued, src, rec, nid, rs.issued, min(kChunk, n - rs.issued * kChunk), lane, lazy);
+                ring_fill<LAZY>(rg, rs.issued, src, rec, nid, rs.issued, min(kChunk, n - rs.issued * kChunk), lane);
                 rs.issued++;
                 if (lazy && rs.issued * kChunk + lane < n) nid = __ldg(ids + rs.issued * kChunk + lane);
             }
@@ -362,7 +365,7 @@ struct BwdSmem {
 
 // U = hitting records whose alpha / skip decisions (all independent of the traversal state) are evaluated together before
 // the short sequential T / R updates: shortens the dependent chain of a warp that walks a long list.
-template <int PPL, int U>
+template <int PPL, int U, bool LAZY>
 __global__ void __launch_bounds__(kRenderThreads)
 render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const unsigned *__restrict__ n_tiles_nonempty,
                   unsigned long long *__restrict__ work_next, int two_ended, int sms, CostOrder co, const uint2 *__restrict__ order_ranges,
@@ -385,7 +388,8 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     ring_init(rg, rs, lane);
     // work list: the measured-cost classes of the forward (heaviest class first) when it grouped its costs for this sub-tile
     // shape, else every sub-tile of the non-empty tiles in population order
-    const bool lazy = __ldcg(lazy_note) != 0u;                      // how the forward of this backward staged its records
+    constexpr bool lazy = LAZY;                                      // the host picks the variant by the rule the forward used
+    (void)lazy_note;
     const bool by_cost = co.cost_acc != nullptr && __ldcg(co.cost_bpt) == (unsigned)ST::kPerTile;
     unsigned cum_end = 0;                                            // lane L: items in classes kCostClasses-1 .. kCostClasses-1-L
     if (by_cost) {
@@ -457,7 +461,7 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
 #pragma unroll
             for (int k = 0; k < kRing; k++) {
                 const int c = nchunks - 1 - k;
-                if (c >= 0) ring_fill(rg, k, src, rec, id0[k], c, min(kChunk, n - c * kChunk), lane, lazy);
+                if (c >= 0) ring_fill<LAZY>(rg, k, src, rec, id0[k], c, min(kChunk, n - c * kChunk), lane);
             }
         }
         rs.issued = min(kRing, nchunks);
@@ -578,7 +582,7 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
             __syncwarp();                                       // every lane has left stage s
             if (rs.issued < nchunks) {
                 const int c2 = nchunks - 1 - rs.issued;
-                ring_fill(rg, rs.issued, src, rec, nid, c2, min(kChunk, n - c2 * kChunk), lane, lazy);
+                ring_fill<LAZY>(rg, rs.issued, src, rec, nid, c2, min(kChunk, n - c2 * kChunk), lane);
                 rs.issued++;
                 if (lazy && rs.issued < nchunks) nid = __ldg(ids + (size_t)(nchunks - 1 - rs.issued) * kChunk + lane);
             }

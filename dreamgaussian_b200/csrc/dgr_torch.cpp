@@ -159,7 +159,7 @@ forward(int64_t H, int64_t W, double tanfovx, double tanfovy, double scale_modif
 // grads: (means3D, means2D, shs | features_dc, colors, opacities, scales, rotations, cov3D, features_rest); undefined where not applicable
 std::vector<Tensor> backward(const std::shared_ptr<State> &st, const OptTensor &gC, const OptTensor &gD, const OptTensor &gA, bool accumulate,
                              const std::vector<OptTensor> &out, const OptTensor &xyz_gradient_accum, const OptTensor &denom,
-                             const OptTensor &max_radii2D) {
+                             const OptTensor &max_radii2D, int64_t push_addr) {
     const c10::cuda::CUDAGuard guard(st->means3D.device());
     const int64_t P = st->g.P, M = st->g.M;
     const auto f32 = st->means3D.options();
@@ -181,7 +181,8 @@ std::vector<Tensor> backward(const std::shared_ptr<State> &st, const OptTensor &
     auto gp = [&](size_t i) -> float * { return g[i].defined() && g[i].numel() > 0 ? g[i].data_ptr<float>() : nullptr; };
     DgrImageGrads gin{fptr(c), fptr(d), fptr(a)};
     DgrGaussianGrads gout{gp(0), gp(1), gp(2), gp(3), gp(4), gp(5), gp(6), gp(7), accumulate ? 1 : 0, gp(8),
-                          fptr_mut(xyz_gradient_accum), fptr_mut(denom), fptr_mut(max_radii2D)};
+                          fptr_mut(xyz_gradient_accum), fptr_mut(denom), fptr_mut(max_radii2D),
+                          reinterpret_cast<const DgrPeerPush *>(push_addr)};      // host struct kept alive by the caller (0 = none)
     void *stream = c10::cuda::getCurrentCUDAStream(st->device).stream();
     check(dgr_backward(&st->s, &st->g, st->geom.data_ptr(), st->binning.data_ptr(), (uint64_t)st->capacity, st->image.data_ptr(),
                        st->radii.data_ptr<int32_t>(), nullptr, &gin, &gout, stream));
@@ -195,7 +196,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         .def_readonly("capacity", &State::capacity)
         .def_readonly("num_rendered", &State::n_inst);
     m.def("forward", &forward, "both forward stages through the C ABI (no arithmetic here)");
-    m.def("backward", &backward, "backward through the C ABI");
+    m.def("backward", &backward, "backward through the C ABI", pybind11::arg("state"), pybind11::arg("grad_color"), pybind11::arg("grad_depth"),
+          pybind11::arg("grad_alpha"), pybind11::arg("accumulate"), pybind11::arg("out"), pybind11::arg("xyz_gradient_accum"),
+          pybind11::arg("denom"), pybind11::arg("max_radii2D"), pybind11::arg("push_addr") = 0);
     m.def("abi_version", []() { return dgr_abi_version(); });
     m.def("set_hint", [](int dev, int64_t P, int H, int W, int64_t cap, bool big) {
         std::lock_guard<std::mutex> lk(g_mu); g_hints[hint_key(dev, P, H, W)] = Hint{cap, big}; });

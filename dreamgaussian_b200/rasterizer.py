@@ -242,12 +242,15 @@ def _host_sync_objects(dev):
 
 
 def backward_impl(state, grad_color, grad_depth, grad_alpha, d_means3D, d_means2D, d_sh, d_col, d_opac, d_scales, d_rot,
-                  d_cov, accumulate=False, d_sh_rest=None, densify=None):
+                  d_cov, accumulate=False, d_sh_rest=None, densify=None, push=None):
     """Runs the backward through the C ABI, writing (or accumulating) into the given gradient tensors.
-    densify = (xyz_gradient_accum, denom, max_radii2D) float32 [P] tensors (any may be None) updated in the same kernel."""
+    densify = (xyz_gradient_accum, denom, max_radii2D) float32 [P] tensors (any may be None) updated in the same kernel.
+    push = a _lib.DgrPeerPush (multi-GPU: rows of Gaussians another rank owns go straight to that rank, include/dgr_b200.h)."""
+    push_addr = ctypes.addressof(push) if push is not None else 0
     if state.fast is not None:
         _FAST.backward(state.fast, grad_color, grad_depth, grad_alpha, bool(accumulate),
-                       [d_means3D, d_means2D, d_sh, d_col, d_opac, d_scales, d_rot, d_cov, d_sh_rest], *(densify or (None, None, None)))
+                       [d_means3D, d_means2D, d_sh, d_col, d_opac, d_scales, d_rot, d_cov, d_sh_rest], *(densify or (None, None, None)),
+                       push_addr)
         return
     lib = _lib.load()
     fr = state.frame
@@ -256,7 +259,7 @@ def backward_impl(state, grad_color, grad_depth, grad_alpha, d_means3D, d_means2
         gin = _lib.DgrImageGrads(_ptr(grad_color), _ptr(grad_depth), _ptr(grad_alpha))
         gout = _lib.DgrGaussianGrads(_ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh), _ptr(d_col), _ptr(d_opac), _ptr(d_scales),
                                      _ptr(d_rot), _ptr(d_cov), 1 if accumulate else 0, _ptr(d_sh_rest),
-                                     *((_ptr(t) for t in densify) if densify is not None else (None, None, None)))
+                                     *((_ptr(t) for t in densify) if densify is not None else (None, None, None)), push_addr or None)
         _lib.check(lib.dgr_backward(ctypes.byref(fr.settings), ctypes.byref(fr.gaussians), _ptr(state.geom), _ptr(state.binning),
                                     ctypes.c_uint64(state.capacity), _ptr(state.image), _ptr(state.radii), _ptr(state.alpha),
                                     ctypes.byref(gin), ctypes.byref(gout), _stream_ptr(dev)))

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DGR_ABI_VERSION 3
+#define DGR_ABI_VERSION 4
 
 /* == GaussianRasterizationSettings, the 12-field NamedTuple built at gs_renderer.py:745-758 == */
 typedef struct DgrSettings {
@@ -75,6 +75,19 @@ typedef struct DgrImageGrads {
     const float *dL_dalpha; /* [1,H,W] */
 } DgrImageGrads;
 
+/* Multi-GPU, view-sharded: lets the per-Gaussian backward deliver gradient rows straight to the rank that OWNS
+ * them.  Gaussian g belongs to rank g / gaussians_per_owner (a positive multiple of 256 with gaussians_per_owner * world >= P).
+ * All the gradient pointers of the call must then lie in ONE local flat buffer, and delta_floats[o] is the distance, in
+ * floats, from any address in that buffer to the same element of THIS rank's slot in rank o's staging area (peer-mapped
+ * symmetric memory); delta_floats[rank] = 0.  With it the backward writes, for every Gaussian of another owner,
+ * (accumulate ? what the local buffer holds : 0) + this view's gradient to the owner instead of to the local buffer — the
+ * reduce-scatter half of the all-reduce rides on the kernel; dgr_peer_reduce_staged() finishes the sum. */
+typedef struct DgrPeerPush {
+    int32_t world, rank;
+    int64_t gaussians_per_owner;
+    int64_t delta_floats[16];
+} DgrPeerPush;
+
 /* == gradients w.r.t. the inputs; any pointer may be NULL (= not wanted) == */
 typedef struct DgrGaussianGrads {
     float *dL_dmeans3D;        /* [P,3]   */
@@ -93,6 +106,7 @@ typedef struct DgrGaussianGrads {
     float *xyz_gradient_accum;
     float *denom;
     float *max_radii2D;
+    const DgrPeerPush *push;   /* NULL: everything goes to the local buffers */
 } DgrGaussianGrads;
 
 /* Scratch sizes.  The caller owns the three scratch buffers (upstream: geomBuffer / binningBuffer / imgBuffer),
@@ -163,6 +177,19 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom, const 
 size_t dgr_peer_flag_bytes(void);
 int dgr_peer_allreduce(const uint64_t *peer_ptrs, int32_t world, int32_t rank, uint64_t n_floats, uint64_t multicast_ptr,
                        const uint64_t *peer_flag_ptrs, uint32_t epoch, void *stream);
+
+/* The all-reduce split in two, its first half fused into the backward (DgrPeerPush): every rank has pushed the rows it does not own;
+ * this call makes rank `push->rank` add the `world` staged copies of ITS rows (stage_ptr: local address of its staging area,
+ * slot s at stage_ptr + s * padded_floats floats; its own contribution is read from its flat buffer peer_ptrs[rank]) in rank order
+ * and publish the sums to every rank's flat buffer (multicast_ptr != 0: multimem.st; else stores to peer_ptrs[w]).  The flat buffer is
+ * n_seg (<= 8) segments [P, seg_stride[k]] starting at float seg_off[k].  peer_flag_ptrs / epoch as for dgr_peer_allreduce (NULL: the
+ * caller synchronises the ranks before and after).  dgr_peer_push_flat does the push for a rank that has no backward to ride on
+ * (no view this iteration): it copies the rows of other owners from `local` (its flat buffer) to their owners. */
+int dgr_peer_reduce_staged(const uint64_t *peer_ptrs, const DgrPeerPush *push, int64_t P, int32_t n_seg, const int64_t *seg_off,
+                           const int32_t *seg_stride, uint64_t stage_ptr, uint64_t padded_floats, uint64_t multicast_ptr,
+                           const uint64_t *peer_flag_ptrs, uint32_t epoch, void *stream);
+int dgr_peer_push_flat(const float *local, const DgrPeerPush *push, int64_t P, int32_t n_seg, const int64_t *seg_off,
+                       const int32_t *seg_stride, void *stream);
 
 /* SURVEY.md §8 row f3 — replaces simple_knn._C.distCUDA2 (/root/reference/simple-knn/spatial.cu:15-26 -> SimpleKNN::knn,
  * simple_knn.cu:185-221; caller gs_renderer.py:341): mean_dists[i] = mean of the squared distances from point i to its 3

@@ -27,7 +27,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libdgr_b200.so does not export %s" % name
     assert set(_lib.EXPORTS) <= set(declared)
-    assert lib.dgr_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.dgr_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_scratch_size_queries_need_no_gpu():
@@ -93,7 +93,7 @@ def test_compiled_host_layer_builds_loads_and_has_no_cpu_path():
     assert os.path.exists(path)
     assert R.set_fast_host(True), "the compiled host layer did not load"
     mod = R._FAST
-    assert mod.abi_version() == 3 and all(hasattr(mod, n) for n in ("forward", "backward", "State", "get_hint", "set_hint"))
+    assert mod.abi_version() == _lib.ABI_VERSION and all(hasattr(mod, n) for n in ("forward", "backward", "State", "get_hint", "set_hint"))
     z = torch.zeros(3)
     with pytest.raises(RuntimeError, match="no CPU path"):
         mod.forward(8, 8, 0.5, 0.5, 1.0, 0, False, False, z, torch.zeros(16), torch.zeros(16), z, torch.zeros(4, 3), None,

@@ -374,17 +374,95 @@ def _allreduce_worker(rank, world, port, out):
     dist.init_process_group("nccl", rank=rank, world_size=world)
     try:
         dev = torch.device("cuda", rank)
-        vsr = multiview.ViewShardedRasterizer(5000, 16, dev)
-        g = torch.Generator(device=dev); g.manual_seed(77 + rank)
-        src = torch.randn(vsr.grads.flat.numel(), device=dev, generator=g)
-        ref = src.clone(); dist.all_reduce(ref)
-        vsr.grads.flat.copy_(src)
-        got = vsr.all_reduce()
-        ok = bool(torch.allclose(got, ref, rtol=1e-6, atol=1e-6))
+        ok, how = True, []
+        for env in ({}, {"DGR_INKERNEL_BARRIERS": "0"}, {"DGR_NO_MULTIMEM": "1"}, {"DGR_PUSH": "1"}):     # default first
+            for k in ("DGR_PUSH", "DGR_INKERNEL_BARRIERS", "DGR_NO_MULTIMEM"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            vsr = multiview.ViewShardedRasterizer(5000, 16, dev)
+            g = torch.Generator(device=dev); g.manual_seed(77 + rank)
+            src = torch.randn(vsr.grads.flat.numel(), device=dev, generator=g)
+            ref = src.clone(); dist.all_reduce(ref)
+            for rep in range(3):
+                vsr.grads.flat.copy_(src)
+                got = vsr.all_reduce()
+                ok = ok and bool(torch.allclose(got, ref, rtol=1e-6, atol=1e-6))
+            how.append(vsr.collective)
+            del vsr
+        for k in ("DGR_PUSH", "DGR_INKERNEL_BARRIERS", "DGR_NO_MULTIMEM"):
+            os.environ.pop(k, None)
+        okt = torch.tensor([int(ok)], device=dev); dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         if rank == 0:
-            open(out, "w").write("%s|%s" % (ok, vsr.collective))
+            open(out, "w").write("%s|%s" % (bool(int(okt)), " / ".join(how)))
     finally:
         dist.destroy_process_group()
+
+
+def _push_worker(rank, world, port, out):
+    """The reduce-scatter half fused into the backward (DgrPeerPush) + dgr_peer_reduce_staged against NCCL on the same
+    per-rank gradients: several views per rank, a rank without a view, Gaussian counts that leave the last owner short or
+    misalign the flat segments (scalar path), and the stand-alone push (dgr_peer_push_flat) bit for bit."""
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    os.environ["DGR_PUSH"] = "1"                                     # the opt-in path under test
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    msgs = []
+    try:
+        dev = torch.device("cuda", rank)
+        t = lambda a: torch.tensor(np.asarray(a, np.float32), device=dev)
+        res, deg = 96, 2
+        for P, nviews in ((5000, (2, 1)), (4999, (1, 3)), (300, (1, 1)), (5000, (2, 0))):
+            cloud = scene.make_cloud(P, deg, seed=3, sigma=0.02)
+            params = {k: t(v) for k, v in cloud.items()}
+            cams = [scene.orbit_camera(5.0 * i, 40.0 * i + 100.0 * rank, 2.0, res, res) for i in range(nviews[rank])]
+            rs = [R.GaussianRasterizationSettings(image_height=res, image_width=res, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=t(np.zeros(3)),
+                                                  scale_modifier=1.0, viewmatrix=t(c.world_view_transform), projmatrix=t(c.full_proj_transform),
+                                                  sh_degree=deg, campos=t(c.camera_center), prefiltered=False, debug=False) for c in cams]
+            g = torch.Generator(device=dev); g.manual_seed(5 + rank)
+            ups = [(torch.randn(3, res, res, device=dev, generator=g), None, torch.randn(1, res, res, device=dev, generator=g)) for _ in cams]
+            ref = multiview.ViewShardedRasterizer(P, (deg + 1) ** 2, dev, peer_allreduce=False)
+            ref.render_views(params, rs, ups)
+            want = ref.all_reduce().clone()                          # NCCL
+            vsr = multiview.ViewShardedRasterizer(P, (deg + 1) ** 2, dev)
+            if not vsr._use_push:
+                msgs.append("push path not active: %s" % getattr(vsr, "_why_nccl", vsr.collective))
+                break
+            for rep in range(2):                                     # twice: the staging area and the flags are reused
+                vsr.render_views(params, rs, ups)
+                got = vsr.all_reduce().clone()
+                scale = float(want.abs().max())
+                err = float((got - want).abs().max())
+                if not err <= 2e-5 * scale:                          # atomics order inside a view differs run to run
+                    msgs.append("P=%d views=%s rep %d: fused push err %.3e of %.3e" % (P, nviews, rep, err, scale))
+            # stand-alone push of a hand-filled buffer: bit-identical to NCCL at two ranks
+            gen = torch.Generator(device=dev); gen.manual_seed(99 + rank)
+            src = torch.randn(vsr.grads.flat.numel(), device=dev, generator=gen)
+            exact = src.clone(); dist.all_reduce(exact)
+            vsr.grads.flat.copy_(src)
+            got = vsr.all_reduce()
+            if not torch.equal(got, exact):
+                msgs.append("P=%d: stand-alone push differs from NCCL by %.3e" % (P, float((got - exact).abs().max())))
+            del vsr, ref
+        every = [None] * world
+        dist.all_gather_object(every, msgs)
+        if rank == 0:
+            flat = ["rank %d: %s" % (r, m) for r, ms in enumerate(every) for m in ms]
+            open(out, "w").write("%s|%s" % (not flat, "; ".join(flat) or "ok"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_push_fused_into_the_backward_matches_nccl(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "r.txt")
+    mp.spawn(_push_worker, args=(2, port, out), nprocs=2, join=True)
+    ok, how = open(out).read().split("|")
+    assert ok == "True", how
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

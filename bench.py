@@ -422,7 +422,7 @@ def collective_check(vsr, dev, rank, world):
 
 def lib_source_stamp():
     from dreamgaussian_b200 import build
-    return build.source_hash()[:16]
+    return build.step_kernel_hash()[:16]
 
 
 def committed_ncu(kind):

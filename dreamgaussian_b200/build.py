@@ -44,6 +44,22 @@ def source_hash():
     return h.hexdigest()
 
 
+STEP_SOURCES = ("dgr_common.cuh", "dgr_preprocess.cuh", "dgr_binning.cuh", "dgr_render.cuh", "dgr_backward.cuh", "dgr_api.cu")
+
+
+def step_kernel_hash():
+    """Hash of what determines the kernels of ONE forward+backward step (their sources, the launcher, the constants, the compiler
+    flags) — the stamp profiles/r2_ncu_kernels.json carries.  The collective, k-NN, field, optimiser and densification kernels are
+    not in that capture and do not invalidate it."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for name in STEP_SOURCES + ("dgr_constants.h",):
+        path = os.path.join(CSRC, name) if not name.endswith(".h") else os.path.join(HERE, "..", "include", name)
+        with open(path, "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
 def is_stale():
     """Content-hash based (mtimes do not survive a repo snapshot to another machine)."""
     if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):

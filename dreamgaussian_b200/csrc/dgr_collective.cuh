@@ -112,6 +112,10 @@ allreduce_p2p_kernel(PeerPtrs peers, PeerFlags flags, unsigned epoch, int world,
     if (BAR) peer_end(flags, world, rank, epoch);
 }
 
+// In-switch variant.  The two halves load the links in OPPOSITE directions: multimem.ld_reduce makes the switch fetch the slice from
+// every GPU (each GPU sends its whole buffer out, receives one reduced slice), multimem.st sends one slice out and brings every
+// rank's slice in.  Issuing all loads and then all stores leaves each direction idle half of the time, so a thread's kUnroll
+// pieces are software-pipelined: the load of piece u+1 is in flight before piece u is stored.
 template <bool BAR>
 __global__ void __launch_bounds__(512)
 allreduce_multimem_kernel(float *mc, PeerFlags flags, unsigned epoch, int world, int rank, size_t n4) {
@@ -122,23 +126,22 @@ allreduce_multimem_kernel(float *mc, PeerFlags flags, unsigned epoch, int world,
     for (size_t i0 = s + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < e; i0 += kUnroll * stride) {
         float4 v[kUnroll];
 #pragma unroll
-        for (int u = 0; u < kUnroll; u++) {
-            const size_t i = i0 + u * stride;
-            if (i < e) {
-                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(mc + 4 * i) : "memory");
+        for (int u = 0; u <= kUnroll; u++) {
+            if (u < kUnroll) {
+                const size_t i = i0 + u * stride;
+                if (i < e)
+                    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(mc + 4 * i) : "memory");
             }
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; u++) {
-            const size_t i = i0 + u * stride;
-            if (i < e)
-                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + 4 * i), "f"(v[u].x), "f"(v[u].y), "f"(v[u].z), "f"(v[u].w) : "memory");
+            if (u > 0) {
+                const size_t i = i0 + (u - 1) * stride;
+                if (i < e)
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + 4 * i), "f"(v[u - 1].x), "f"(v[u - 1].y), "f"(v[u - 1].z), "f"(v[u - 1].w) : "memory");
+            }
         }
     }
     if (BAR) peer_end(flags, world, rank, epoch);
 }
-
 
 // ---- reduce-scatter by pushing, fused into the per-Gaussian backward (opt-in: DGR_PUSH=1) -----------------------------------------
 // MEASURED NEGATIVE at 2 GPUs (profiles/r2_phases_n2_push.json): the per-Gaussian backward is ONE wave of CTAs whose stores all

@@ -32,7 +32,7 @@ def main(rep):
         a["inst"] += float(r[idx["smsp__inst_executed.sum"]].replace(",", ""))
         t = float(r[idx["gpu__time_duration.sum"]].replace(",", "")); a["us"] += t / 1000.0 if units[idx["gpu__time_duration.sum"]] in ("ns", "nsecond") else t
         a["issue"] += float(r[idx["smsp__issue_active.avg.pct_of_peak_sustained_active"]].replace(",", ""))
-    out = {"lib_source_hash": build.source_hash()[:16], "source": "ncu --set full --clock-control none, %s" % os.path.basename(rep),
+    out = {"lib_source_hash": build.step_kernel_hash()[:16], "source": "ncu --set full --clock-control none, %s" % os.path.basename(rep),
            "workload": "100k Gaussians, 800x800, SH degree 3, forward+backward, opacity=trained, anisotropic",
            "dram_bytes_per_launch": {k: a["dram"] / a["n"] for k, a in acc.items()},
            "warp_inst_per_launch": {k: a["inst"] / a["n"] for k, a in acc.items()},

@@ -116,7 +116,7 @@ allreduce_p2p_kernel(PeerPtrs peers, PeerFlags flags, unsigned epoch, int world,
 // every GPU (each GPU sends its whole buffer out, receives one reduced slice), multimem.st sends one slice out and brings every
 // rank's slice in.  Issuing all loads and then all stores leaves each direction idle half of the time, so a thread's kUnroll
 // pieces are software-pipelined: the load of piece u+1 is in flight before piece u is stored.
-template <bool BAR>
+template <bool BAR, bool PIPE>
 __global__ void __launch_bounds__(512)
 allreduce_multimem_kernel(float *mc, PeerFlags flags, unsigned epoch, int world, int rank, size_t n4) {
     if (BAR) peer_begin(flags, world, rank, epoch);
@@ -125,6 +125,22 @@ allreduce_multimem_kernel(float *mc, PeerFlags flags, unsigned epoch, int world,
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i0 = s + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < e; i0 += kUnroll * stride) {
         float4 v[kUnroll];
+        if (!PIPE) {                                   // all loads, then all stores (A/B reference: DGR_AR_PIPELINE=0)
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) {
+                const size_t i = i0 + u * stride;
+                if (i < e)
+                    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(mc + 4 * i) : "memory");
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) {
+                const size_t i = i0 + u * stride;
+                if (i < e)
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + 4 * i), "f"(v[u].x), "f"(v[u].y), "f"(v[u].z), "f"(v[u].w) : "memory");
+            }
+            continue;
+        }
 #pragma unroll
         for (int u = 0; u <= kUnroll; u++) {
             if (u < kUnroll) {

@@ -10,7 +10,8 @@ import numpy as np, torch, torch.distributed as dist
 from dreamgaussian_b200 import _lib, multiview, scene
 from dreamgaussian_b200.rasterizer import GaussianRasterizationSettings
 
-ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=120); a = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=120)
+ap.add_argument("--modes", default="", help="comma-separated subset of the modes below"); a = ap.parse_args()
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
 if world > 1:
@@ -56,8 +57,10 @@ del vsr
 if world > 1:
     for mode, env in (("allreduce_inkernel", {}), ("allreduce_hostbar", {"DGR_INKERNEL_BARRIERS": "0"}), ("allreduce_p2p", {"DGR_NO_MULTIMEM": "1"}),
                       ("push_inkernel", {"DGR_PUSH": "1"}), ("push_hostbar", {"DGR_PUSH": "1", "DGR_INKERNEL_BARRIERS": "0"}),
-                      ("nccl", {"DGR_NO_PEER": "1"})):
-        for k in ("DGR_INKERNEL_BARRIERS", "DGR_NO_MULTIMEM", "DGR_NO_PEER", "DGR_PUSH"):
+                      ("multimem_forced", {"DGR_FORCE_MULTIMEM": "1"}), ("nccl", {"DGR_NO_PEER": "1"})):
+        if a.modes and mode not in a.modes.split(","):
+            continue
+        for k in ("DGR_INKERNEL_BARRIERS", "DGR_NO_MULTIMEM", "DGR_NO_PEER", "DGR_PUSH", "DGR_FORCE_MULTIMEM"):
             os.environ.pop(k, None)
         os.environ.update(env)
         vsr = multiview.ViewShardedRasterizer(P, (deg + 1) ** 2, dev)

@@ -50,11 +50,30 @@ constexpr int kSigBegin = 0, kSigEnd = kMaxPeers, kSigCount = 2 * kMaxPeers;    
 
 // (Polling with relaxed loads and one fence after the word has arrived, signalling with relaxed stores behind an explicit fence,
 // measured 9 us SLOWER than the acquire / release forms below at 2 GPUs — profiles/r2_phases_n2_*.json.)
+// A peer that never arrives (its process died, the ranks disagree on the number of calls) must not hang the GPU: after
+// kPeerWaitNs of polling the kernel traps, which surfaces as a CUDA error on the host instead of a stuck device.
+constexpr unsigned long long kPeerWaitNs = 20ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void wait_epoch(const unsigned *word, unsigned epoch) {
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    while ((int)(ld_acquire_sys_u32(word) - epoch) < 0) {
+        if ((++spins & 0x3fffu) == 0) {
+            const unsigned long long t = global_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > kPeerWaitNs) __trap();
+        }
+    }
+}
+
 __device__ __forceinline__ void peer_begin(const PeerFlags &flags, int world, int rank, unsigned epoch) {
     if ((int)threadIdx.x < world) {
         if (blockIdx.x == 0) st_release_sys_u32(flags.p[threadIdx.x] + kSigBegin + rank, epoch);
-        const unsigned *mine = flags.p[rank] + kSigBegin + threadIdx.x;
-        while ((int)(ld_acquire_sys_u32(mine) - epoch) < 0) { }
+        wait_epoch(flags.p[rank] + kSigBegin + threadIdx.x, epoch);
     }
     __syncthreads();
 }
@@ -72,8 +91,7 @@ __device__ __forceinline__ void peer_end(const PeerFlags &flags, int world, int 
     __syncthreads();
     if (last && (int)threadIdx.x < world) {
         st_release_sys_u32(flags.p[threadIdx.x] + kSigEnd + rank, epoch);
-        const unsigned *mine = flags.p[rank] + kSigEnd + threadIdx.x;
-        while ((int)(ld_acquire_sys_u32(mine) - epoch) < 0) { }
+        wait_epoch(flags.p[rank] + kSigEnd + threadIdx.x, epoch);
     }
 }
 

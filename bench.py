@@ -648,13 +648,70 @@ def run_ours(a, rank, world, local_rank):
             c1.record(); torch.cuda.synchronize(dev)
             link[nm] = nbytes * 5 / (c0.elapsed_time(c1) * 1e-3) / 1e9
         step_ms = float(ms_e.item()) / e2e_steps
+        # the overlap, shown (there is no nsys in this image): a short untimed pass of the same pipeline with a timing event on
+        # either side of every upload / compute / download on its own stream -> start and end of each stage on one clock
+        timeline = None
+        if world == 1:
+            TL = 12
+            marks = {k: [] for k in ("up", "comp", "down")}
+
+            def staged(kind, stream, fn, i):
+                b_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                fn(i, lambda: b_.record(stream), lambda: e_.record(stream))
+                marks[kind].append((b_, e_))
+
+            def up_t(i, mark_b, mark_e):
+                r = i % RING
+                with torch.cuda.stream(s_up):
+                    s_up.wait_event(ev_comp[r]); mark_b(); dev_in[r].copy_(host_in, non_blocking=True); mark_e(); ev_up[r].record(s_up)
+
+            def comp_t(i, mark_b, mark_e):
+                r = i % RING
+                vs = local_views(i)
+                with torch.cuda.stream(s_comp):
+                    s_comp.wait_event(ev_up[r]); s_comp.wait_event(ev_down[r]); mark_b()
+                    rings[r].render_views(dev_views[r], [settings[v] for v in vs], [ups_d[v % len(ups_d)] for v in vs])
+                    mark_e(); ev_comp[r].record(s_comp)
+
+            def down_t(i, mark_b, mark_e):
+                r = i % RING
+                with torch.cuda.stream(s_down):
+                    s_down.wait_event(ev_comp[r]); mark_b(); host_out[r][:nflat].copy_(rings[r].grads.flat, non_blocking=True); mark_e(); ev_down[r].record(s_down)
+
+            torch.cuda.synchronize(dev)
+            origin = torch.cuda.Event(enable_timing=True); origin.record()
+            for st_ in (s_up, s_comp, s_down):
+                st_.wait_event(origin)
+            staged("up", s_up, up_t, 200)
+            for i in range(200, 200 + TL):
+                if i + 1 < 200 + TL:
+                    staged("up", s_up, up_t, i + 1)
+                staged("comp", s_comp, comp_t, i)
+                staged("down", s_down, down_t, i)
+            torch.cuda.synchronize(dev)
+            iv = {k: [(origin.elapsed_time(b_), origin.elapsed_time(e_)) for b_, e_ in v] for k, v in marks.items()}
+
+            def covered(a, others):          # fraction of interval a that some interval of `others` covers
+                tot = 0.0
+                for b_, e_ in others:
+                    tot += max(0.0, min(a[1], e_) - max(a[0], b_))
+                return min(1.0, tot / max(a[1] - a[0], 1e-9))
+            mid = slice(3, TL - 1)            # steady state
+            timeline = {
+                "steps": TL, "ms_mean": {k: round(float(np.mean([e_ - b_ for b_, e_ in v[mid]])), 4) for k, v in iv.items()},
+                "period_ms": round((iv["down"][TL - 2][1] - iv["down"][3][1]) / (TL - 5), 4),
+                "compute_under_upload": round(float(np.mean([covered(c_, iv["up"]) for c_ in iv["comp"][mid]])), 3),
+                "compute_under_download": round(float(np.mean([covered(c_, iv["down"]) for c_ in iv["comp"][mid]])), 3),
+                "upload_under_download": round(float(np.mean([covered(u_, iv["down"]) for u_ in iv["up"][mid]])), 3),
+                "intervals_ms_first_6_steps": {k: [[round(b_, 3), round(e_, 3)] for b_, e_ in v[:6]] for k, v in iv.items()},
+                "note": "CUDA events around every stage on its own stream, one clock; fractions = share of the stage's duration during which a stage of the other kind was running"}
         e2e = {"value": P * vpg * world * e2e_steps / (float(ms_e.item()) * 1e-3), "unit": "splats/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": step_ms, "steps": e2e_steps,
                "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / e2e_steps,
                "copies_per_step": {"h2d": 1, "d2h": 2}, "link_gbs_alone": link,
                "link_gbs_in_pipeline": {"h2d": h2d / (step_ms * 1e-3) / 1e9, "d2h": d2h / (step_ms * 1e-3) / 1e9},
                "host_buffers_numa_local": bool(hostmem.gpu_local_cpus(dev)), "loss": float(host_out[(100 + e2e_steps - 1) % RING][nflat]),
-               "collective": rings[0].collective if world > 1 else "none",
+               "collective": rings[0].collective if world > 1 else "none", "timeline": timeline,
                "note": "public API (ViewShardedRasterizer.render_views [+ all_reduce]); packed inputs from / flat gradient + loss to "
                        "pinned host memory every step, one copy per direction (+4 bytes of loss); upload, compute and download of "
                        "consecutive steps overlap on 3 streams"}

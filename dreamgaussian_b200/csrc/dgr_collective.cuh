@@ -45,7 +45,7 @@ __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
 //     in your buffer" and stays until every peer has said the same — the kernel's completion then means the whole sum is
 //     here, and all other blocks have long left the SMs.
 // (A first version paired block b of every rank with block b of every peer, 2 x grid remote flag stores and system fences per
-// rank: 20 us slower than host-launched barrier kernels at 2 GPUs, profiles/r2_bench_n2_inkernel.json.)
+// rank: 20 us slower than host-launched barrier kernels at 2 GPUs, profiles/r2_earlier/r2_bench_n2_inkernel.json.)
 constexpr int kSigBegin = 0, kSigEnd = kMaxPeers, kSigCount = 2 * kMaxPeers;      // word offsets inside a rank's flag area
 
 // (Polling with relaxed loads and one fence after the word has arrived, signalling with relaxed stores behind an explicit fence,

@@ -134,18 +134,48 @@ int check_gaussians(const DgrSettings *s, const DgrGaussians *g) {
 
 constexpr size_t kMaxTileSmem = 200 * 1024;      // tile-histogram rows live in shared memory: up to 51200 tiles
 
+// tuning knobs of dgr_set_tuning bits 24-26 (atomics, like the ones further down)
+std::atomic<int> g_stage_fwd{1}, g_stage_bwd{1};   // per-Gaussian kernels: inputs staged through shared memory by bulk TMA (dgr_preprocess.cuh)
+std::atomic<int> g_rowsum{1};                  // backward render, step 2: per-row form of the dy moments (dgr_render.cuh, ROWSUM)
+
+// Can the per-Gaussian kernels stage their inputs with bulk TMA (dgr_preprocess.cuh)?  SH + scale / rotation inputs, every base
+// pointer 16-byte aligned (cp.async.bulk), P at least one full warp.
+inline bool stage_inputs_ok(const DgrGaussians *g, bool raw) {
+    if (!g->shs || g->cov3D_precomp || !g->scales || !g->rotations || g->P < 32) return false;
+    uintptr_t bits = (uintptr_t)g->means3D | (uintptr_t)g->scales | (uintptr_t)g->rotations | (uintptr_t)g->opacities | (uintptr_t)g->shs;
+    if (raw && g->M > 1) bits |= (uintptr_t)g->shs_rest;
+    return (bits & 15u) == 0;
+}
+constexpr size_t kMaxKernelSmem = 227 * 1024;
+
 template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
 void launch_pre_fwd(const DgrSettings *s, const DgrGaussians *g, int *radii, char *geom, const GeomLayout &L, unsigned *tile_count,
                     cudaStream_t st) {
     unsigned *run_matrix = reinterpret_cast<unsigned *>(geom + L.off_runs);
-    const size_t smem = (size_t)L.tiles * 4;
+    const size_t hist = (size_t)L.tiles * 4;
+    if constexpr (HAS_SH && !HAS_COV) {
+        // inputs staged through shared memory by bulk TMA: [tile histogram | 8 warps x 32 x (44 + 12 M) bytes]
+        const size_t stage_off = align_up(hist, 128);
+        const size_t smem = stage_off + (size_t)(kPreThreads / 32) * stage_warp_floats(g->M) * 4;
+        if (g_stage_fwd.load() && stage_inputs_ok(g, RAW) && smem + 1024 <= kMaxKernelSmem) {
+            if (smem > 48 * 1024)
+                cudaFuncSetAttribute(preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV, RAW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            launch_k(preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV, RAW, true>, dim3(L.nblocks), dim3(kPreThreads), smem, st, false,
+                g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
+                s->campos, g->means3D, g->shs, g->shs_rest, g->colors_precomp, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii,
+                reinterpret_cast<Rec *>(geom + L.off_rec), reinterpret_cast<unsigned *>(geom + L.off_touched),
+                tile_count, run_matrix, L.tiles, L.iters, (int)stage_off);
+            return;
+        }
+    }
+    const size_t smem = hist;
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    launch_k(preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV, RAW>, dim3(L.nblocks), dim3(kPreThreads), smem, st, false,
+        cudaFuncSetAttribute(preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV, RAW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    launch_k(preprocess_fwd_kernel<DEG, HAS_SH, HAS_COV, RAW, false>, dim3(L.nblocks), dim3(kPreThreads), smem, st, false,
         g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
         s->campos, g->means3D, g->shs, g->shs_rest, g->colors_precomp, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii,
         reinterpret_cast<Rec *>(geom + L.off_rec), reinterpret_cast<unsigned *>(geom + L.off_touched),
-        tile_count, run_matrix, L.tiles, L.iters);
+        tile_count, run_matrix, L.tiles, L.iters, 0);
 }
 
 template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
@@ -158,11 +188,26 @@ void launch_pre_bwd(const DgrSettings *s, const DgrGaussians *g, const int *radi
         push.per = (int)o->push->gaussians_per_owner;
         for (int w = 0; w < o->push->world && w < kMaxPeers; w++) push.delta[w] = o->push->delta_floats[w];
     }
-    launch_k(preprocess_bwd_kernel<DEG, HAS_SH, HAS_COV, RAW>, dim3(nb), dim3(kPreThreads), 0, st, true,
+    if constexpr (HAS_SH && !HAS_COV) {
+        // inputs staged by bulk TMA; the same per-warp slice of dynamic shared memory is the warp's output image afterwards
+        const int wfl = max(stage_warp_floats(g->M), kStageFloats);
+        const size_t smem = (size_t)(kPreThreads / 32) * wfl * 4;
+        if (g_stage_bwd.load() && stage_inputs_ok(g, RAW) && smem + 1024 <= kMaxKernelSmem) {
+            if (smem > 48 * 1024)
+                cudaFuncSetAttribute(preprocess_bwd_kernel<DEG, HAS_SH, HAS_COV, RAW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            launch_k(preprocess_bwd_kernel<DEG, HAS_SH, HAS_COV, RAW, true>, dim3(nb), dim3(kPreThreads), smem, st, true,
+                g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
+                s->campos, g->means3D, g->shs, g->shs_rest, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii, touched, grad_rec,
+                o->dL_dmeans3D, o->dL_dmeans2D, o->dL_dshs, o->dL_dcolors_precomp, o->dL_dopacities, o->dL_dscales, o->dL_drotations,
+                o->dL_dcov3D_precomp, o->dL_dshs_rest, o->xyz_gradient_accum, o->denom, o->max_radii2D, o->accumulate, push, wfl);
+            return;
+        }
+    }
+    launch_k(preprocess_bwd_kernel<DEG, HAS_SH, HAS_COV, RAW, false>, dim3(nb), dim3(kPreThreads), 0, st, true,
         g->P, g->M, s->image_height, s->image_width, s->tanfovx, s->tanfovy, s->scale_modifier, s->viewmatrix, s->projmatrix,
         s->campos, g->means3D, g->shs, g->shs_rest, g->opacities, g->scales, g->rotations, g->cov3D_precomp, radii, touched, grad_rec,
         o->dL_dmeans3D, o->dL_dmeans2D, o->dL_dshs, o->dL_dcolors_precomp, o->dL_dopacities, o->dL_dscales, o->dL_drotations,
-        o->dL_dcov3D_precomp, o->dL_dshs_rest, o->xyz_gradient_accum, o->denom, o->max_radii2D, o->accumulate, push);
+        o->dL_dcov3D_precomp, o->dL_dshs_rest, o->xyz_gradient_accum, o->denom, o->max_radii2D, o->accumulate, push, 0);
 }
 
 #define DGR_DISPATCH(FN, ...)                                                                              \
@@ -300,6 +345,9 @@ int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order) {
     g_two_ended = (tile_order >> 20) & 1;               // bit 20: work queue consumed from both ends (experiment; measured slower)
     g_cost_order = (tile_order >> 21) & 1 ? 0 : 1;      // bit 21: backward work in tile-population order instead of measured cost
     g_lazy = (tile_order >> 22) & 3;                    // bits 22-23: record staging 0 = auto, 1 = always the sorted copy, 2 = always by id
+    g_stage_fwd = (tile_order >> 24) & 1 ? 0 : 1;       // bit 24 / 25: per-Gaussian forward / backward kernel reads its inputs with
+    g_stage_bwd = (tile_order >> 25) & 1 ? 0 : 1;       // per-thread global loads instead of bulk-TMA staging (A/B switch)
+    g_rowsum = (tile_order >> 26) & 1 ? 0 : 1;          // bit 26: backward render step 2 in the per-pixel form (A/B switch; <1,2> non-lazy only)
     return 0;
 }
 
@@ -507,6 +555,21 @@ int dgr_backward(const DgrSettings *s, const DgrGaussians *g, void *geom_v, cons
         // the record staging follows the rule the forward applied to the same capacity (dgr_forward_render)
         const int lz = g_lazy.load();
         const bool lazy = lz == 2 || (lz == 0 && (size_t)capacity * sizeof(Rec) > 2 * dv->l2_bytes);
+        if (ppl == 1 && ub != 1 && !lazy && !g_rowsum.load()) {       // A/B: the default shape with the per-pixel step 2
+#define DGR_BWD_OLD_ render_bwd_kernel<1, 2, false, false>
+            const size_t smem_ = sizeof(BwdSmem<1>) * kRenderWarps;
+            int grid_ = min(persistent_grid(dv, DGR_BWD_OLD_, kRenderThreads, smem_), (tiles * SubTile<1>::kPerTile + kRenderWarps - 1) / kRenderWarps);
+            if (g_cta_bwd.load() > 0) grid_ = min(grid_, g_cta_bwd.load() * dv->sms);
+            DGR_KERNEL("render_bwd", st, s->debug,
+                       launch_k(DGR_BWD_OLD_, dim3((unsigned)grid_), dim3(kRenderThreads), smem_, st, false, H, W, IL.gx,
+                                reinterpret_cast<const unsigned *>(image + IL.off_order), &work->n_nonempty, bwd_next, g_two_ended.load(), dv->sms, co,
+                                reinterpret_cast<const uint2 *>(image + IL.off_oranges),
+                                reinterpret_cast<const Rec *>(binning + BL.off_rec), reinterpret_cast<const Rec *>(geom + GL.off_rec),
+                                (const unsigned *)&work->lazy, reinterpret_cast<const unsigned *>(binning + BL.off_ids),
+                                s->bg, reinterpret_cast<const float *>(image + IL.off_finalT),
+                                reinterpret_cast<const unsigned *>(image + IL.off_ncontrib), gin->dL_dcolor, gin->dL_ddepth, gin->dL_dalpha, grad_rec));
+#undef DGR_BWD_OLD_
+        } else
         if (ppl == 1) { if (ub == 1) DGR_RENDER_BWD(1, 1); else DGR_RENDER_BWD(1, 2); }     // default <1,2> (in-pipeline sweep, profiles/r2_sweep.txt)
         else { if (ub == 2) DGR_RENDER_BWD(2, 2); else DGR_RENDER_BWD(2, 1); }
 #undef DGR_RENDER_BWD_L

@@ -132,7 +132,10 @@ __device__ __forceinline__ void store_sh_grads(float *__restrict__ dL_dshs, int 
     }
 }
 
-template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
+// STAGE: the warp's inputs arrive by bulk TMA in its slice of dynamic shared memory (see dgr_preprocess.cuh, "Input staging");
+// once every lane has its values in registers the same slice becomes the warp's output image (warp_flush), so the staged
+// variant needs 8 x 32 x (44 + 12 M) bytes per CTA (59 KB at degree 3: three CTAs per SM, as before) and no static stage.
+template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW, bool STAGE = false>
 __global__ void __launch_bounds__(kPreThreads, 3)
 preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, float scale_modifier,
                       const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
@@ -145,19 +148,34 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                       float *__restrict__ dL_dcolors, float *__restrict__ dL_dopacities, float *__restrict__ dL_dscales,
                       float *__restrict__ dL_drotations, float *__restrict__ dL_dcov3D, float *__restrict__ dL_dshs_rest,
                       float *__restrict__ xyz_gradient_accum, float *__restrict__ denom, float *__restrict__ max_radii2D,
-                      int accumulate, PeerPush push) {
+                      int accumulate, PeerPush push, int warp_smem_floats) {
     __shared__ FrameConsts fc;
-    __shared__ __align__(16) float s_stage[(kPreThreads / 32) * kStageFloats];
+    __shared__ __align__(16) float s_stage[STAGE ? 4 : (kPreThreads / 32) * kStageFloats];
+    __shared__ uint64_t s_stage_bar[kPreThreads / 32];
+    extern __shared__ __align__(128) float s_dyn[];              // STAGE: 8 warps x warp_smem_floats (>= kStageFloats)
+    static_assert(!STAGE || (HAS_SH && !HAS_COV), "input staging: SH + scale / rotation inputs only");
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    bool staged = false;                                         // warp-uniform: all 32 Gaussians of this warp exist and are staged
+    if (STAGE) {
+        const int g0 = (int)(blockIdx.x * blockDim.x + (threadIdx.x & ~31u));
+        uint64_t *wbar = &s_stage_bar[threadIdx.x >> 5];
+        staged = g0 + 32 <= P;
+        if ((threadIdx.x & 31) == 0) {
+            mbar_init(wbar, 1); mbar_fence_init();
+            if (staged) stage_issue<RAW>(s_dyn + (threadIdx.x >> 5) * warp_smem_floats, wbar, g0, M, means3D, scales, rotations, opacities, shs, shs_rest);
+        }
+        __syncwarp();
+    }
     load_frame(fc, viewmatrix, projmatrix, HAS_SH ? campos : nullptr);
     __syncthreads();
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
     const bool acc = accumulate != 0;
     const bool in_range = g < P;
     // gradient rows of Gaussians another rank owns go to that rank's staging slot (what the local buffer has accumulated over
     // this rank's earlier views of the iteration + this view); every row is written then, culled Gaussians included
     const long long delta = push.per > 0 ? push.delta[(blockIdx.x * blockDim.x) / (unsigned)push.per] : 0;
     const bool pushing = delta != 0;
-    float *ws = s_stage + (threadIdx.x >> 5) * kStageFloats;        // this warp's output image (see warp_flush)
+    float *ws = STAGE ? s_dyn + (threadIdx.x >> 5) * warp_smem_floats
+                      : s_stage + (threadIdx.x >> 5) * kStageFloats;   // this warp's output image (see warp_flush)
     const int lane = threadIdx.x & 31;
     // every input of this Gaussian is requested up front (one memory round trip; none of it depends on the backward render)
     int radius_in = 0;
@@ -168,6 +186,18 @@ preprocess_bwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
     if (in_range) {
         radius_in = radii[g];
         touched_in = __ldg(touched + g);
+    }
+    if (staged) {
+        mbar_wait(&s_stage_bar[threadIdx.x >> 5], 0u);
+        p = make_float3(ws[kStgMean + 3 * lane], ws[kStgMean + 3 * lane + 1], ws[kStgMean + 3 * lane + 2]);
+        s_in = make_float3(ws[kStgScale + 3 * lane], ws[kStgScale + 3 * lane + 1], ws[kStgScale + 3 * lane + 2]);
+        q_in = *reinterpret_cast<const float4 *>(ws + kStgRot + 4 * lane);
+        o_in = ws[kStgOp + lane];
+        if (RAW) { if (DEG > 0) lds_sh_row<DEG, 1>(ws + kStgSh + 96 + lane * (M - 1) * 3, ((M - 1) & 3) == 0, shc); }
+        else lds_sh_row<DEG>(ws + kStgSh + lane * M * 3, (M & 3) == 0, shc);
+    }
+    if (STAGE) __syncwarp();             // every lane has its inputs in registers: from here on the slice is the warp's output image
+    if (in_range && !staged) {
         p = make_float3(__ldg(means3D + 3 * (size_t)g), __ldg(means3D + 3 * (size_t)g + 1), __ldg(means3D + 3 * (size_t)g + 2));
         if (HAS_COV) {
 #pragma unroll

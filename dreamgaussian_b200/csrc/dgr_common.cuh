@@ -163,6 +163,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ float rcp_approx(float x) {
     float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
+// index of the most significant set bit (x != 0): one FLO instead of the FLO + two integer ops of 31 - __clz(x)
+__device__ __forceinline__ int bfind_u32(unsigned x) { int r; asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x)); return r; }
 __device__ __forceinline__ void red_add_f32(float *addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }

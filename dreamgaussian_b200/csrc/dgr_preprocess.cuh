@@ -116,6 +116,58 @@ __device__ __forceinline__ void load_sh_row(const float *row, bool vec, float (&
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Input staging of the per-Gaussian kernels (bulk TMA).  A thread of these kernels needs 44 + 12 M bytes of ITS Gaussian:
+// read per thread, a warp-wide 128-bit load of the SH rows touches 32 different 128-byte lines (row stride 12 M bytes), so the
+// 12 loads of a degree-3 row cost 12 x 32 L1 wavefronts per warp and the kernel is bound by the load/store unit long before
+// HBM.  But the 32 Gaussians of a warp are ONE contiguous run in each input array: lane 0 fetches the warp's five runs with
+// five cp.async.bulk copies (completion on the warp's own mbarrier, no CTA-level coupling) and every lane then picks its
+// values out of shared memory.  Layout of a warp's staging area, in floats (every piece starts 16-byte aligned):
+//   [0, 96) means3D | [96, 192) scales | [192, 320) rotations | [320, 352) opacities | [352, 352 + 96 M) SH rows
+//   (raw parameters: [352, 448) _features_dc, [448, 448 + 96 (M - 1)) _features_rest)
+// Used for full warps (32 valid Gaussians) when every base pointer is 16-byte aligned; a partial warp at the end of the cloud
+// and unaligned inputs take the per-thread loads.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int kStgMean = 0, kStgScale = 96, kStgRot = 192, kStgOp = 320, kStgSh = 352;
+__host__ __device__ inline int stage_warp_floats(int M) { return 32 * (11 + 3 * M); }
+
+// lane 0 of a warp: start the copies of the 32 Gaussians [g0, g0 + 32) into the warp's staging area
+template <bool RAW>
+__device__ __forceinline__ void stage_issue(float *ws, uint64_t *bar, int g0, int M, const float *means3D, const float *scales,
+                                            const float *rotations, const float *opacities, const float *shs, const float *shs_rest) {
+    const uint32_t sh_bytes = RAW ? 384u : 384u * (uint32_t)M, rest_bytes = (RAW && M > 1) ? 384u * (uint32_t)(M - 1) : 0u;
+    mbar_expect_tx(bar, 384u + 384u + 512u + 128u + sh_bytes + rest_bytes);
+    tma_bulk_g2s(ws + kStgMean, means3D + 3 * (size_t)g0, 384u, bar);
+    tma_bulk_g2s(ws + kStgScale, scales + 3 * (size_t)g0, 384u, bar);
+    tma_bulk_g2s(ws + kStgRot, rotations + 4 * (size_t)g0, 512u, bar);
+    tma_bulk_g2s(ws + kStgOp, opacities + (size_t)g0, 128u, bar);
+    if (RAW) {
+        tma_bulk_g2s(ws + kStgSh, shs + 3 * (size_t)g0, 384u, bar);                                   // _features_dc [P, 1, 3]
+        if (rest_bytes) tma_bulk_g2s(ws + kStgSh + 96, shs_rest + (size_t)g0 * (M - 1) * 3, rest_bytes, bar);
+    } else {
+        tma_bulk_g2s(ws + kStgSh, shs + (size_t)g0 * M * 3, sh_bytes, bar);
+    }
+}
+
+// A staged SH row (coefficients FIRST .. NB-1 of lane's Gaussian) into registers; same register image as load_sh_row.
+template <int DEG, int FIRST = 0>
+__device__ __forceinline__ void lds_sh_row(const float *row, bool vec, float (&c)[48]) {
+    constexpr int N = 3 * ((DEG + 1) * (DEG + 1) - FIRST);
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < (N + 3) / 4; i++) {
+            const float4 v = *reinterpret_cast<const float4 *>(row + 4 * i);
+            c[4 * i] = v.x;
+            if (4 * i + 1 < 48) c[4 * i + 1] = v.y;
+            if (4 * i + 2 < 48) c[4 * i + 2] = v.z;
+            if (4 * i + 3 < 48) c[4 * i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) c[i] = row[i];
+    }
+}
+
 // GaussianModel activations (gs_renderer.py:127-138, :196-216), applied in registers when the caller passes the raw
 // parameters (DgrGaussians.activations): scaling = exp, opacity = sigmoid, rotation = F.normalize (eps 1e-12).
 __device__ __forceinline__ float act_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
@@ -168,7 +220,7 @@ __device__ __forceinline__ void project_geo(const FrameConsts &fc, const float3 
     g.cyy = g.T1[0] * ST1[0] + g.T1[1] * ST1[1] + g.T1[2] * ST1[2] + DGR_COV2D_LOWPASS;
 }
 
-template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW>
+template <int DEG, bool HAS_SH, bool HAS_COV, bool RAW, bool STAGE = false>
 __global__ void __launch_bounds__(kPreThreads, 3)
 preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, float scale_modifier,
                       const float *__restrict__ viewmatrix, const float *__restrict__ projmatrix,
@@ -178,28 +230,69 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
                       const float *__restrict__ scales, const float *__restrict__ rotations,
                       const float *__restrict__ cov3D_precomp,
                       int *__restrict__ radii, Rec *__restrict__ rec, unsigned *__restrict__ touched_out,
-                      unsigned *__restrict__ tile_count, unsigned *__restrict__ run_matrix, int tiles, int gpb_iters) {
+                      unsigned *__restrict__ tile_count, unsigned *__restrict__ run_matrix, int tiles, int gpb_iters, int stage_off) {
     // Per-block tile histogram in shared memory (native integer smem atomics); at the end every touched tile's count is
     // added to the per-tile totals with ONE global atomic per (block, tile) — not one per instance — and what the atomic
     // returns (where this block's run starts inside the tile's range) goes into the block's row of the run matrix.
-    extern __shared__ unsigned s_hist[];
+    extern __shared__ __align__(128) unsigned s_hist[];
     __shared__ FrameConsts fc;
+    __shared__ uint64_t s_stage_bar[kPreThreads / 32];
+    static_assert(!STAGE || (HAS_SH && !HAS_COV), "input staging: SH + scale / rotation inputs only");
     pdl_trigger();                       // the tile scan may become resident now (it waits for this grid's completion)
+    // STAGE: this warp's inputs of the first block iteration are on their way before anything else happens
+    const int lane = threadIdx.x & 31;
+    float *wstage = STAGE ? reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(s_hist) + stage_off) + (threadIdx.x >> 5) * stage_warp_floats(M)
+                          : nullptr;
+    uint64_t *wbar = &s_stage_bar[threadIdx.x >> 5];
+    unsigned stage_phase = 0;
+    bool stage_inflight = false;         // warp-uniform: the copies of the NEXT block iteration have been started
+    if (STAGE) {
+        if (lane == 0) { mbar_init(wbar, 1); mbar_fence_init(); }
+        __syncwarp();
+        const int g0 = (int)(blockIdx.x * gpb_iters * kPreThreads + (threadIdx.x & ~31u));
+        stage_inflight = g0 + 32 <= P;
+        if (stage_inflight && lane == 0) stage_issue<RAW>(wstage, wbar, g0, M, means3D, scales, rotations, opacities, shs, shs_rest);
+    }
     load_frame(fc, viewmatrix, projmatrix, HAS_SH ? campos : nullptr);
     for (int t = threadIdx.x; t < tiles; t += kPreThreads) s_hist[t] = 0u;
     __syncthreads();
     for (int it = 0; it < gpb_iters; it++) {
     const int g = (int)((blockIdx.x * gpb_iters + it) * kPreThreads + threadIdx.x);
     unsigned touched = 0, clamp_flags = 0;
+    // every input of this Gaussian is requested before anything is computed (one memory round trip)
+    float3 p = make_float3(0.f, 0.f, 0.f);
+    float S6[6];
+    float3 s_in = make_float3(0.f, 0.f, 0.f);
+    float4 q_in = make_float4(1.f, 0.f, 0.f, 0.f);
+    float o_in = 0.f;
+    float shc[48], dc0 = 0.f, dc1 = 0.f, dc2 = 0.f, pc0 = 0.f, pc1 = 0.f, pc2 = 0.f;
+    const bool staged = STAGE && stage_inflight;                      // warp-uniform: all 32 Gaussians of this warp exist and are staged
+    if (staged) {
+        mbar_wait(wbar, stage_phase); stage_phase ^= 1u;
+        p = make_float3(wstage[kStgMean + 3 * lane], wstage[kStgMean + 3 * lane + 1], wstage[kStgMean + 3 * lane + 2]);
+        s_in = make_float3(wstage[kStgScale + 3 * lane], wstage[kStgScale + 3 * lane + 1], wstage[kStgScale + 3 * lane + 2]);
+        q_in = *reinterpret_cast<const float4 *>(wstage + kStgRot + 4 * lane);
+        o_in = wstage[kStgOp + lane];
+        if (RAW) {
+            dc0 = wstage[kStgSh + 3 * lane]; dc1 = wstage[kStgSh + 3 * lane + 1]; dc2 = wstage[kStgSh + 3 * lane + 2];
+            if (DEG > 0) lds_sh_row<DEG, 1>(wstage + kStgSh + 96 + lane * (M - 1) * 3, ((M - 1) & 3) == 0, shc);
+        } else lds_sh_row<DEG>(wstage + kStgSh + lane * M * 3, (M & 3) == 0, shc);
+    }
+    if (STAGE) {
+        __syncwarp();                    // every lane has its values in registers: the staging area is free for the next block iteration
+        stage_inflight = false;
+        if (it + 1 < gpb_iters) {
+            const int g0 = (int)((blockIdx.x * gpb_iters + it + 1) * kPreThreads + (threadIdx.x & ~31u));
+            stage_inflight = g0 + 32 <= P;
+            if (stage_inflight && lane == 0) stage_issue<RAW>(wstage, wbar, g0, M, means3D, scales, rotations, opacities, shs, shs_rest);
+        }
+    }
     if (g < P) {
         int radius_out = 0;
         Rec r;
         r.q0 = make_float4(0.f, 0.f, 0.f, 0.f); r.q1 = r.q0; r.q2 = r.q0;
-        // every input of this Gaussian is requested before anything is computed (one memory round trip)
-        const float3 p = make_float3(__ldg(means3D + 3 * (size_t)g), __ldg(means3D + 3 * (size_t)g + 1), __ldg(means3D + 3 * (size_t)g + 2));
-        float S6[6];
-        float3 s_in = make_float3(0.f, 0.f, 0.f);
-        float4 q_in = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (!staged) {
+        p = make_float3(__ldg(means3D + 3 * (size_t)g), __ldg(means3D + 3 * (size_t)g + 1), __ldg(means3D + 3 * (size_t)g + 2));
         if (HAS_COV) {
 #pragma unroll
             for (int i = 0; i < 6; i++) S6[i] = __ldg(cov3D_precomp + 6 * (size_t)g + i);
@@ -207,8 +300,7 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
             s_in = make_float3(__ldg(scales + 3 * (size_t)g), __ldg(scales + 3 * (size_t)g + 1), __ldg(scales + 3 * (size_t)g + 2));
             q_in = ldg_f4(rotations + 4 * (size_t)g);
         }
-        const float o_in = __ldg(opacities + g);
-        float shc[48], dc0 = 0.f, dc1 = 0.f, dc2 = 0.f, pc0 = 0.f, pc1 = 0.f, pc2 = 0.f;
+        o_in = __ldg(opacities + g);
         if (HAS_SH) {
             if (RAW) {          // _features_dc [P,1,3] + _features_rest [P,M-1,3]: no torch.cat copy
                 dc0 = __ldg(shs + 3 * (size_t)g); dc1 = __ldg(shs + 3 * (size_t)g + 1); dc2 = __ldg(shs + 3 * (size_t)g + 2);
@@ -216,6 +308,7 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
             } else load_sh_row<DEG>(shs + (size_t)g * M * 3, (M & 3) == 0, shc);
         } else {
             pc0 = __ldg(colors_precomp + 3 * (size_t)g); pc1 = __ldg(colors_precomp + 3 * (size_t)g + 1); pc2 = __ldg(colors_precomp + 3 * (size_t)g + 2);
+        }
         }
         const float tzc = p.x * fc.V[2] + p.y * fc.V[6] + p.z * fc.V[10] + fc.V[14];
         if (tzc > DGR_NEAR_CULL_Z) {

@@ -365,7 +365,10 @@ struct BwdSmem {
 
 // U = hitting records whose alpha / skip decisions (all independent of the traversal state) are evaluated together before
 // the short sequential T / R updates: shortens the dependent chain of a warp that walks a long list.
-template <int PPL, int U, bool LAZY>
+// ROWSUM = the step-2 accumulation uses that the 8 pixels a lane covers per pass lie on ONE pixel row: dy is constant over them, so
+// only sum u, sum u dx, sum u dx^2 run per pixel and the three dy moments follow from them per row (5 instead of 8 floating-point
+// instructions per (record, pixel) on the u side).  ROWSUM = false keeps the per-pixel form (A/B: dgr_set_tuning bit 26).
+template <int PPL, int U, bool LAZY, bool ROWSUM = true>
 __global__ void __launch_bounds__(kRenderThreads)
 render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order, const unsigned *__restrict__ n_tiles_nonempty,
                   unsigned long long *__restrict__ work_next, int two_ended, int sms, CostOrder co, const uint2 *__restrict__ order_ranges,
@@ -477,6 +480,35 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
             const float ccx = __shfl_sync(0xffffffffu, cap_cx, my_r), ccy = __shfl_sync(0xffffffffu, cap_cy, my_r);
             float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f, v9 = 0.f;
             const float *row = &sm.uw[my_r][0];
+            if (ROWSUM) {
+                static_assert(kPixPerLane % 8 == 0, "a lane's pixels come in rows of 8");
+#pragma unroll
+                for (int g8 = 0; g8 < kPixPerLane / 8; g8++) {
+                    const int kb = my_q * kPixPerLane + 8 * g8;               // first pixel of this row of 8 (p * 32 + lane of step 1)
+                    const int pl = kb & 31, pp = kb >> 5;
+                    const float dxb = ccx - (float)((PPL == 4 && (pp & 1)) ? 8 : 0);
+                    const float dy = ccy - (float)((pl >> 3) + ((PPL == 4) ? (pp >> 1) * 4 : pp * 4));
+                    float s0 = 0.f, s1 = 0.f, s3 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        const float4 t = *reinterpret_cast<const float4 *>(row + 2 * (kb + i));   // (u, w) of pixels kb + i, kb + i + 1
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const float u = e ? t.z : t.x, w = e ? t.w : t.y;
+                            const float dx = dxb - (float)(i + e);
+                            const float4 g = sm.g[kb + i + e];
+                            const float udx = u * dx;
+                            s0 += u; s1 += udx; s3 = __fmaf_rn(udx, dx, s3);
+                            v6 = __fmaf_rn(w, g.x, v6); v7 = __fmaf_rn(w, g.y, v7); v8 = __fmaf_rn(w, g.z, v8); v9 = __fmaf_rn(w, g.w, v9);
+                        }
+                    }
+                    if (g8 == 0) { v0 = s0; v1 = s1; v3 = s3; v2 = dy * s0; v4 = dy * s1; v5 = (dy * dy) * s0; }
+                    else {
+                        v0 += s0; v1 += s1; v3 += s3;
+                        v2 = __fmaf_rn(dy, s0, v2); v4 = __fmaf_rn(dy, s1, v4); v5 = __fmaf_rn(dy * dy, s0, v5);
+                    }
+                }
+            } else {
 #pragma unroll
             for (int i = 0; i < kPixPerLane; i += 2) {
                 const int k = my_q * kPixPerLane + i;                     // pixel index of the sub-tile (p * 32 + lane of step 1)
@@ -494,6 +526,7 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
                     v3 = __fmaf_rn(udx, dx, v3); v4 = __fmaf_rn(udx, dy, v4); v5 = __fmaf_rn(udy, dy, v5);
                     v6 = __fmaf_rn(w, g.x, v6); v7 = __fmaf_rn(w, g.y, v7); v8 = __fmaf_rn(w, g.z, v8); v9 = __fmaf_rn(w, g.w, v9);
                 }
+            }
             }
 #pragma unroll
             for (int o = kBatch; o < 32; o <<= 1) {
@@ -529,7 +562,7 @@ render_bwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     js[u] = 0;
-                    if (mask) { js[u] = 31 - __clz(mask); mask &= ~(1u << js[u]); nh = u + 1; }
+                    if (mask) { js[u] = bfind_u32(mask); mask &= ~(1u << js[u]); nh = u + 1; }      // last record of the chunk first
                 }
                 float agv[U][PPL], av[U][PPL], rcx[U], rcy[U], dep[U], cr[U], cg[U], cb[U];
                 bool okv[U][PPL], any_ok[U];

@@ -150,6 +150,10 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom, 
  *   bit 21       backward work in tile-population order instead of the cost the forward measured
  *   bits 22-23   record staging of the render kernels: 0 = automatic (by Gaussian id when the sorted copy would exceed twice
  *                the L2 size), 1 = always the sorted copy, 2 = always by id
+ *   bit 24 / 25  the per-Gaussian forward / backward kernel reads its inputs with per-thread global loads instead of staging
+ *                each warp's 32 contiguous Gaussians through shared memory with bulk TMA (A/B switch; the staged path needs
+ *                SH + scale / rotation inputs and 16-byte aligned base pointers and is otherwise not taken anyway)
+ *   bit 26       step 2 of the backward render kernel in its per-pixel form (A/B switch; default sub-tile shape only)
  * the other bits are accepted and ignored. */
 int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order);
 

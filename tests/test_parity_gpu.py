@@ -173,6 +173,38 @@ def test_forward_is_deterministic_and_tuning_independent():
             assert torch.equal(a, b)          # bit-identical: per-pixel arithmetic does not depend on the launch shape
 
 
+@pytest.mark.parametrize("case", ["plain", "raw"])
+def test_staged_and_per_thread_input_paths_and_both_step2_forms_agree(case):
+    """dgr_set_tuning bits 24 / 25: the per-Gaussian kernels read their inputs through bulk-TMA staging (full warps) or with
+    per-thread loads — same registers, same arithmetic.  Bit 26: step 2 of the backward render in its per-row or per-pixel
+    form — same sums in a different association: float32 round-off only.  P is not a multiple of 32, so the staged
+    runs mix both input paths in one launch."""
+    lib = _lib.load()
+    if case == "plain":
+        s, i = h.make_case(P=20011, res=400, deg=3)
+        run = lambda: h.run_cuda(s, i, g)
+    else:
+        s, i = h.make_case(P=9007, res=200, deg=2)
+        raw = scene.to_raw_parameters(i)
+        run = lambda: h.run_cuda_raw(s, raw, g)
+    g = h.upstream_grads(s["image_height"], s["image_width"])
+    try:
+        base = run()                                                  # defaults: staged inputs, per-row step 2
+        # (gradients: the backward render accumulates the moments with red.global.add in whatever order the warps arrive, so two
+        #  runs of the SAME variant already differ in the last bits; the images and radii are deterministic)
+        for bits in (1 << 24, 1 << 25, (1 << 24) | (1 << 25), 1 << 26, 7 << 24):
+            _lib.check(lib.dgr_set_tuning(1, 1, 1 | bits))
+            other = run()
+            for k in ("color", "depth", "alpha", "radii"):
+                assert np.array_equal(base[k], other[k]), (bits, k)
+            for k, v in base["grads"].items():
+                scale = float(np.abs(v).max())
+                if scale > 0:
+                    assert float(np.abs(v - other["grads"][k]).max()) <= 2e-5 * scale, (bits, k)
+    finally:
+        _lib.check(lib.dgr_set_tuning(1, 1, 1))
+
+
 def test_padded_sh_storage_with_lower_active_degree():
     """gs_renderer.py:806 passes get_features ([P, (max_sh_degree+1)^2, 3]) with sh_degree=active_sh_degree: the storage can
     hold more coefficients than the active degree reads.  Unused coefficients change nothing and get zero gradient."""

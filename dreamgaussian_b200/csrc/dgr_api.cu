@@ -136,6 +136,7 @@ constexpr size_t kMaxTileSmem = 200 * 1024;      // tile-histogram rows live in 
 
 // tuning knobs of dgr_set_tuning bits 24-26 (atomics, like the ones further down)
 std::atomic<int> g_stage_fwd{1}, g_stage_bwd{1};   // per-Gaussian kernels: inputs staged through shared memory by bulk TMA (dgr_preprocess.cuh)
+std::atomic<int> g_sort_fine{0};               // per-tile sort with 2048 instead of 1024 depth buckets (A/B, bit 28)
 std::atomic<int> g_rowsum{1};                  // backward render, step 2: per-row form of the dy moments (dgr_render.cuh, ROWSUM)
 
 // Can the per-Gaussian kernels stage their inputs with bulk TMA (dgr_preprocess.cuh)?  SH + scale / rotation inputs, every base
@@ -254,6 +255,7 @@ std::atomic<int> g_lazy{0};            // record staging of the render kernels: 
 std::atomic<int> g_cta_fwd{0}, g_cta_bwd{0};   // persistent CTAs per SM of the render kernels (0 = as many as fit)
 
 using SmS = SortSmem<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>;
+using SmSF = SortSmem<kSortSmallThreads, kSortSmallCap, kSortSmallBucketsFine>;
 using SmB = SortSmem<kSortBigThreads, kSortBigCap, kSortBigBuckets>;
 
 // Per-DEVICE launch state: cudaFuncSetAttribute (dynamic shared memory above 48 KB) and the occupancy-derived persistent
@@ -281,7 +283,8 @@ DevInfo *dev_info() {
     int l2 = 0;
     if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev) == cudaSuccess && l2 > 0) d.l2_bytes = (size_t)l2;
     cudaError_t e = cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxTileSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sort_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmS::bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sort_gather_kernel<kSortSmallBuckets>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmS::bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sort_gather_kernel<kSortSmallBucketsFine>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmSF::bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_sort_gather_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SmB::bytes);
     if (e != cudaSuccess) { fail((int)e, "cudaFuncSetAttribute", cudaGetErrorString(e)); return nullptr; }
     d.ready = true;
@@ -347,6 +350,7 @@ int dgr_set_tuning(int ppl_fwd, int ppl_bwd, int tile_order) {
     g_lazy = (tile_order >> 22) & 3;                    // bits 22-23: record staging 0 = auto, 1 = always the sorted copy, 2 = always by id
     g_stage_fwd = (tile_order >> 24) & 1 ? 0 : 1;       // bit 24 / 25: per-Gaussian forward / backward kernel reads its inputs with
     g_stage_bwd = (tile_order >> 25) & 1 ? 0 : 1;       // per-thread global loads instead of bulk-TMA staging (A/B switch)
+    g_sort_fine = (tile_order >> 28) & 1;               // bit 28: per-tile sort with 2048 depth buckets (A/B switch)
     g_rowsum = (tile_order >> 26) & 1 ? 0 : 1;          // bit 26: backward render step 2 in the per-pixel form (A/B switch; <1,2> non-lazy only)
     return 0;
 }
@@ -444,10 +448,17 @@ int dgr_forward_render(const DgrSettings *s, const DgrGaussians *g, void *geom_v
     const int lz = g_lazy.load();
     const bool lazy = lz == 2 || (lz == 0 && (size_t)capacity * sizeof(Rec) > 2 * dv->l2_bytes);
     if (g->P > 0 && capacity > 0) {
-        const int sort_grid = min(tiles, persistent_grid(dv, tile_sort_gather_kernel, kSortSmallThreads, SmS::bytes));
-        DGR_KERNEL("tile_sort_gather", st, s->debug,
-                   launch_k(tile_sort_gather_kernel, dim3(sort_grid), dim3(kSortSmallThreads), SmS::bytes, st, true, (const TileWork *)work,
-                            reinterpret_cast<const uint2 *>(image + IL.off_oranges), keys, rec, ids, recs, lazy ? 0 : 1));
+        if (g_sort_fine.load()) {
+            const int sort_grid = min(tiles, persistent_grid(dv, tile_sort_gather_kernel<kSortSmallBucketsFine>, kSortSmallThreads, SmSF::bytes));
+            DGR_KERNEL("tile_sort_gather", st, s->debug,
+                       launch_k(tile_sort_gather_kernel<kSortSmallBucketsFine>, dim3(sort_grid), dim3(kSortSmallThreads), SmSF::bytes, st, true, (const TileWork *)work,
+                                reinterpret_cast<const uint2 *>(image + IL.off_oranges), keys, rec, ids, recs, lazy ? 0 : 1));
+        } else {
+            const int sort_grid = min(tiles, persistent_grid(dv, tile_sort_gather_kernel<kSortSmallBuckets>, kSortSmallThreads, SmS::bytes));
+            DGR_KERNEL("tile_sort_gather", st, s->debug,
+                       launch_k(tile_sort_gather_kernel<kSortSmallBuckets>, dim3(sort_grid), dim3(kSortSmallThreads), SmS::bytes, st, true, (const TileWork *)work,
+                                reinterpret_cast<const uint2 *>(image + IL.off_oranges), keys, rec, ids, recs, lazy ? 0 : 1));
+        }
         if (flags & DGR_FLAG_BIG_TILES)
             DGR_KERNEL("tile_sort_gather_big", st, s->debug,
                        launch_k(tile_sort_gather_big_kernel, dim3(dv->big_grid), dim3(kSortBigThreads), SmB::bytes, st, true, (const TileWork *)work,

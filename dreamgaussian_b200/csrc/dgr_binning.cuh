@@ -233,16 +233,30 @@ emit_instances_kernel(int P, int gx, int tiles, int gpb_iters, int nblocks, cons
     unsigned long long run = 0;
     for (int w = 0; w < warp; w++) run += s_part[w];
     const unsigned *row = run_matrix + (size_t)blockIdx.x * tiles;
-    for (int t0 = w_lo; t0 < w_hi; t0 += 32) {
-        const int t = t0 + lane;
-        const unsigned c = t < w_hi ? __ldcg(tile_count + t) : 0u;
-        const unsigned rr = t < w_hi ? __ldcg(row + t) : 0u;
-        unsigned inc = c;
+    // (the totals and run-matrix entries of kE 32-tile pieces are requested before the first of them is scanned: the scans form
+    //  a dependent chain through `run`, and one L2 round trip per piece would otherwise sit in front of every link of it)
+    constexpr int kE = 4;
+    for (int t0 = w_lo; t0 < w_hi; t0 += 32 * kE) {
+        unsigned cj[kE], rj[kE];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
-        const unsigned long long start = run + (inc - c);
-        if (t < w_hi) s_off[t] = (unsigned)(start < cap ? start : cap) + rr;
-        run += __shfl_sync(0xffffffffu, inc, 31);
+        for (int j = 0; j < kE; j++) {
+            const int t = t0 + 32 * j + lane;
+            cj[j] = t < w_hi ? __ldcg(tile_count + t) : 0u;
+            rj[j] = t < w_hi ? __ldcg(row + t) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < kE; j++) {
+            if (t0 + 32 * j < w_hi) {                                     // warp-uniform
+                const int t = t0 + 32 * j + lane;
+                const unsigned c = cj[j];
+                unsigned inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+                const unsigned long long start = run + (inc - c);
+                if (t < w_hi) s_off[t] = (unsigned)(start < cap ? start : cap) + rj[j];
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
     }
     __syncthreads();
     const unsigned cap32 = (unsigned)cap;
@@ -413,12 +427,13 @@ __device__ __forceinline__ void sort_gather_tile(const uint2 r, unsigned long lo
     }
 }
 
-constexpr int kSortSmallThreads = 512, kSortSmallBuckets = 1024;
+constexpr int kSortSmallThreads = 512, kSortSmallBuckets = 1024, kSortSmallBucketsFine = 2048;   // (Fine: A/B, dgr_set_tuning bit 28)
 constexpr int kSortBigThreads = 1024, kSortBigCap = 12288, kSortBigBuckets = 2048;     // 96 KB of keys + 16 KB of bucket tables
 
 // Persistent grid over the NON-EMPTY tiles in issue order (heaviest first, dealt round-robin to the CTAs): CTA c sorts entries
 // c, c + G, c + 2G ... of the ordered range list the emit kernel's metadata block wrote; the next entry's range is already
 // in flight while a tile is being sorted.  Tiles beyond kSortSmallCap are left to the big-tile kernel.
+template <int NBK>
 __global__ void __launch_bounds__(kSortSmallThreads, 4)
 tile_sort_gather_kernel(const TileWork *__restrict__ work, const uint2 *__restrict__ order_ranges, unsigned long long *__restrict__ keys,
                         const Rec *__restrict__ rec, unsigned *__restrict__ ids_sorted, Rec *__restrict__ rec_sorted, int gather) {
@@ -433,7 +448,7 @@ tile_sort_gather_kernel(const TileWork *__restrict__ work, const uint2 *__restri
         const uint2 rnext = inext < n_tiles ? __ldcg(order_ranges + inext) : make_uint2(0u, 0u);
         const int n = (int)(r.y - r.x);
         if (n > 0 && n <= kSortSmallCap)
-            sort_gather_tile<kSortSmallThreads, kSortSmallCap, kSortSmallBuckets>(r, keys, rec, ids_sorted, rec_sorted, s_sort, gather != 0);
+            sort_gather_tile<kSortSmallThreads, kSortSmallCap, NBK>(r, keys, rec, ids_sorted, rec_sorted, s_sort, gather != 0);
         i = inext; r = rnext;
     }
 }

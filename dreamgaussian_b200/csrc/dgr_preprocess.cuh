@@ -399,7 +399,7 @@ preprocess_fwd_kernel(int P, int M, int H, int W, float tanfovx, float tanfovy, 
     }
     __syncthreads();
     unsigned *row = run_matrix + (size_t)blockIdx.x * tiles;
-    constexpr int kB = 8;                                // atomics in flight per thread
+    constexpr int kB = 12;                               // atomics in flight per thread (800 x 800: all 2500 tiles in ONE round trip)
     for (int t0 = threadIdx.x; t0 < tiles; t0 += kPreThreads * kB) {
         unsigned c[kB], got[kB];
 #pragma unroll

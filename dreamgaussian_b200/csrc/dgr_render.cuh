@@ -123,11 +123,18 @@ __device__ __forceinline__ int ring_wait(WarpRing &rg, RingState &rs, int seq) {
 // meet: the heavy items are then in flight a few at a time per sub-partition and get re-dealt as warps free up, instead of
 // all starting at once and fixing every sub-partition's load for the whole kernel.  (two_ended = 0: everybody takes from
 // the heavy end.)  An atomicAdd returns both words as they were, so every item is handed out exactly once.
-__device__ __forceinline__ unsigned queue_take(unsigned long long *ctr, bool light, unsigned n) {
+// `zero` receives bit 63 of the counter — always 0 (it would take 2^31 light-end takes), but only known once the atomic has
+// returned: adding it to an address makes that access wait for THIS request instead of being scheduled in front of it.
+__device__ __forceinline__ unsigned queue_take(unsigned long long *ctr, bool light, unsigned n, unsigned &zero) {
     const unsigned long long old = atomicAdd(ctr, light ? (1ull << 32) : 1ull);
     const unsigned h = (unsigned)old, l = (unsigned)(old >> 32);
+    zero = l >> 31;
     if ((unsigned long long)h + l >= n) return 0xffffffffu;
     return light ? n - 1u - l : h;
+}
+__device__ __forceinline__ unsigned queue_take(unsigned long long *ctr, bool light, unsigned n) {
+    unsigned z;
+    return queue_take(ctr, light, n, z);
 }
 
 // Measured-cost ordering of the backward.  How long a sub-tile's list really is (early termination!) is only known after
@@ -191,12 +198,17 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
     const bool light = two_ended && (((blockIdx.x / (unsigned)sms) + (threadIdx.x >> 5)) & 1u);
     bool queue_phase = true;
     unsigned item = 0, empty_next = n_queue + warp_global;
+    // cost filing of the previous item (lane 0): the list position comes from an atomic whose round trip is as long as the queue's,
+    // so it is only looked at here, after the NEXT item has been requested (the two round trips overlap instead of adding up)
+    bool pend = false;
+    unsigned pend_pos = 0, pend_base = 0, pend_val = 0;
     for (;;) {
+        // (the item is taken when the warp is ready for it, not earlier: reserving the next item ahead of time would
+        //  hand out the whole queue at the start and leave nothing to balance with — measured 58 -> 72 us)
+        unsigned fetched = 0, zero = 0;
+        if (queue_phase && lane == 0) fetched = queue_take(work_next, light, n_queue, zero);
+        if (pend) { co.cls_items[(size_t)pend_base + pend_pos + zero] = pend_val; pend = false; }
         if (queue_phase) {
-            // (the item is taken when the warp is ready for it, not earlier: reserving the next item ahead of time would
-            //  hand out the whole queue at the start and leave nothing to balance with — measured 58 -> 72 us)
-            unsigned fetched = 0;
-            if (lane == 0) fetched = queue_take(work_next, light, n_queue);
             item = __shfl_sync(0xffffffffu, fetched, 0);
             if (item >= n_queue) queue_phase = false;
         }
@@ -329,20 +341,22 @@ render_fwd_kernel(int H, int W, int gx, const unsigned *__restrict__ tile_order,
             for (int p = 0; p < PPL; p++) contrib = contrib || (last[p] > 0u);
             contrib = __any_sync(0xffffffffu, contrib);
             if (lane == 0) {
-                const int bpt = 8 / co.bwd_ppl, parts = co.bwd_ppl / PPL;                 // forward items per backward item
+                const int parts = co.bwd_ppl / PPL;                                       // forward items per backward item
                 const int bsub = co.bwd_ppl == 1 ? ((wy0 & 15) >> 2) * 2 + ((wx0 & 15) >> 3)
                                                  : ((wy0 & 15) >> 3) * 2 + ((wx0 & 15) >> 3);
                 const unsigned mine = contrib ? cost + 1u : 0u;
-                const unsigned old = atomicAdd(co.cost_acc + (size_t)tile * 8 + bsub, (mine << 2) | 1u);
-                if ((int)(old & 3u) + 1 == parts) {
-                    const unsigned total = (old >> 2) + mine;
-                    if (total > 0u) {
-                        const int cls = cost_class(total);
-                        const unsigned pos = atomicAdd(co.cls_count + cls, 1u);
-                        co.cls_items[(size_t)cls * co.tiles * 8 + pos] = ot * 8u + (unsigned)bsub;
-                    }
+                unsigned total = mine;
+                bool complete = true;
+                if (parts > 1) {                  // several forward items feed one backward item: the last one to arrive files it
+                    const unsigned old = atomicAdd(co.cost_acc + (size_t)tile * 8 + bsub, (mine << 2) | 1u);
+                    complete = (int)(old & 3u) + 1 == parts;
+                    total = (old >> 2) + mine;
                 }
-                (void)bpt;
+                if (complete && total > 0u) {
+                    const int cls = cost_class(total);
+                    pend_pos = atomicAdd(co.cls_count + cls, 1u);                        // (looked at after the next item was requested)
+                    pend_base = (unsigned)cls * (unsigned)co.tiles * 8u; pend_val = ot * 8u + (unsigned)bsub; pend = true;
+                }
             }
         }
         __syncwarp();

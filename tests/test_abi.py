@@ -39,6 +39,16 @@ def test_scratch_size_queries_need_no_gpu():
     assert lib.dgr_geom_bytes(0, 16, 16) > 0 and lib.dgr_binning_bytes(0, 16, 16) > 0
 
 
+def test_tuning_word_is_validated_and_its_switch_bits_are_accepted():
+    """dgr_set_tuning: sub-tile shapes are checked, the bit field (A/B switches up to bit 28, include/dgr_b200.h) is accepted and
+    needs no GPU; the defaults are restored."""
+    lib = _lib.load()
+    assert lib.dgr_set_tuning(3, 1, 1) != 0 and b"ppl" in lib.dgr_last_error()
+    for bits in (1 << 3, 1 << 20, 1 << 21, 2 << 22, 1 << 24, 1 << 25, 1 << 26, 1 << 28, (7 << 24) | (1 << 28), 0x7fffffff):
+        assert lib.dgr_set_tuning(1, 2, 1 | bits) == 0
+    assert lib.dgr_set_tuning(1, 1, 1) == 0
+
+
 def test_python_surface_matches_reference_operator():
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     # the 12 fields the reference passes by keyword at gs_renderer.py:745-758, in the op's order

@@ -7,6 +7,7 @@
 // libdgr_b200.so, which this module links.  Mirrors rasterize_gaussians / rasterize_gaussians_backward of the reference
 // package's ext.cpp [EXT] (called from /root/reference/gs_renderer.py:800-809 through GaussianRasterizer).
 #include <torch/extension.h>
+#include <cstdint>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 #include <cuda_runtime.h>
@@ -27,7 +28,11 @@ float *fptr_mut(const OptTensor &t) { return (t.has_value() && t->defined() && t
 Tensor dev_f32(const Tensor &t, const char *name) {
     TORCH_CHECK(t.is_cuda(), name, " is on ", t.device(), ": this rasterizer has no CPU path (it runs as sm_100a CUDA kernels in libdgr_b200.so)");
     Tensor r = t.scalar_type() == torch::kFloat32 ? t : t.to(torch::kFloat32);
-    return r.contiguous();
+    r = r.contiguous();
+    // the kernels read rotations / SH rows with 128-bit loads and stage inputs with bulk TMA: a view that starts off a 16-byte
+    // boundary gets its own (aligned) allocation
+    if (r.numel() > 0 && (reinterpret_cast<uintptr_t>(r.data_ptr()) & 15u) != 0) r = r.clone(at::MemoryFormat::Contiguous);
+    return r;
 }
 OptTensor opt_f32(const OptTensor &t, const char *name) {
     if (!t.has_value() || !t->defined() || (t->numel() == 0 && t->dim() <= 1)) return c10::nullopt;

@@ -98,7 +98,15 @@ def _dev_f32(t: torch.Tensor, name: str) -> torch.Tensor:
             "%s is on %s: this rasterizer has no CPU path (it runs as sm_100a CUDA kernels in libdgr_b200.so)" % (name, t.device))
     if t.dtype != torch.float32:
         t = t.float()
-    return t.contiguous()
+    return _aligned16(t.contiguous())
+
+
+def _aligned16(t: torch.Tensor) -> torch.Tensor:
+    """The kernels read rotations / SH rows with 128-bit loads and stage their inputs with bulk TMA: a contiguous view that starts
+    off a 16-byte boundary (e.g. ``flat[1:].view(P, 4)``) gets its own allocation, which is aligned."""
+    if t.numel() > 0 and t.data_ptr() % 16 != 0:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
 
 
 def _opt(t, name):

@@ -40,7 +40,11 @@ typedef struct DgrSettings {
     const float *campos;     /* [3]   as given by the caller (= -c2w[:3,3], gs_renderer.py:671) */
 } DgrSettings;
 
-/* == the per-Gaussian inputs of GaussianRasterizer.forward (gs_renderer.py:800-809); float32, contiguous == */
+/* == the per-Gaussian inputs of GaussianRasterizer.forward (gs_renderer.py:800-809); float32, contiguous ==
+ * Alignment: `rotations`, and `shs` / `shs_rest` when their rows are a multiple of 16 bytes (M % 4 == 0, (M - 1) % 4 == 0), are read
+ * with 128-bit loads and must be 16-byte aligned — what every device allocation is; the two host layers of this repository
+ * re-allocate a view that is not (rasterizer.py::_dev_f32, dgr_torch.cpp::dev_f32).  When ALL of means3D / scales / rotations /
+ * opacities / shs (/ shs_rest) are 16-byte aligned the per-Gaussian kernels stage them with bulk TMA (see dgr_set_tuning). */
 typedef struct DgrGaussians {
     int32_t P;                   /* number of Gaussians */
     int32_t M;                   /* SH coefficients per channel in `shs` (= shs.shape[1]); 0 if shs == NULL */

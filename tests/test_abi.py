@@ -49,6 +49,19 @@ def test_tuning_word_is_validated_and_its_switch_bits_are_accepted():
     assert lib.dgr_set_tuning(1, 1, 1) == 0
 
 
+def test_misaligned_input_views_get_their_own_aligned_allocation():
+    """The kernels read rotations / SH rows with 128-bit loads (include/dgr_b200.h, DgrGaussians): the host layer re-allocates a
+    contiguous view that starts off a 16-byte boundary and leaves aligned tensors alone (no copy)."""
+    import torch
+    from dreamgaussian_b200 import rasterizer as R
+    flat = torch.arange(41, dtype=torch.float32)
+    view = flat[1:].view(10, 4)
+    assert view.is_contiguous() and view.data_ptr() % 16 != 0
+    fixed = R._aligned16(view)
+    assert fixed.data_ptr() % 16 == 0 and torch.equal(fixed, view)
+    assert R._aligned16(flat) is flat and R._aligned16(flat[:0]).numel() == 0
+
+
 def test_python_surface_matches_reference_operator():
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     # the 12 fields the reference passes by keyword at gs_renderer.py:745-758, in the op's order

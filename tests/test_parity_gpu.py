@@ -210,6 +210,23 @@ def test_staged_and_per_thread_input_paths_and_both_step2_forms_agree(case):
         _lib.check(lib.dgr_set_tuning(1, 1, 1))
 
 
+def test_input_views_that_start_off_a_16_byte_boundary_are_accepted():
+    """Contiguous views into a larger buffer (``flat[1:].view(P, K)``: 4-byte aligned only) give the same result as fresh tensors:
+    the host layer re-allocates them (the kernels use 128-bit loads and bulk-TMA staging, include/dgr_b200.h)."""
+    s, i = h.make_case(P=1500, res=96, deg=3, sigma=0.04, elev=10, azim=50)
+    ti, rs = _torch_inputs(i), _settings(s)
+    off = {}
+    for k, v in ti.items():
+        flat = torch.empty(v.numel() + 1, dtype=torch.float32, device=v.device)
+        flat[1:] = v.reshape(-1)
+        off[k] = flat[1:].view(v.shape)
+        assert off[k].data_ptr() % 16 != 0 and off[k].is_contiguous()
+    a = R.GaussianRasterizer(rs)(means2D=torch.zeros_like(ti["means3D"]), **ti)
+    b = R.GaussianRasterizer(rs)(means2D=torch.zeros_like(ti["means3D"]), **off)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
 def test_padded_sh_storage_with_lower_active_degree():
     """gs_renderer.py:806 passes get_features ([P, (max_sh_degree+1)^2, 3]) with sh_degree=active_sh_degree: the storage can
     hold more coefficients than the active degree reads.  Unused coefficients change nothing and get zero gradient."""
